@@ -1,0 +1,37 @@
+// Host-visible table of compiled onesweep tile configurations (one table per key width x value width).
+#pragma once
+
+#include "common.cuh"
+
+namespace b200rs
+{
+
+typedef cudaError_t (*onesweep_launch_fn)(const PassArgs& args, unsigned grid, cudaStream_t stream);
+
+struct OnesweepConfig
+{
+  int threads;
+  int items_per_thread;
+  int rank_algo;
+  int min_blocks;
+  int tile_items;
+  size_t smem_bytes;
+  onesweep_launch_fn launch;
+};
+
+// index 0 is the default for the (key_bytes, value_bytes) combination
+const OnesweepConfig* onesweep_configs_k1(int value_bytes, int* count);
+const OnesweepConfig* onesweep_configs_k2(int value_bytes, int* count);
+const OnesweepConfig* onesweep_configs_k4(int value_bytes, int* count);
+const OnesweepConfig* onesweep_configs_k8(int value_bytes, int* count);
+
+cudaError_t launch_histogram(
+  const void* keys, unsigned long long n, int key_bytes, unsigned long long* bins, int passes, int begin_bit,
+  int end_bit, const KeyXform& xf, int sm_count, cudaStream_t stream);
+cudaError_t launch_scan_bins(unsigned long long* bins, int passes, cudaStream_t stream);
+
+cudaError_t launch_splitter_ranks(
+  const void* sorted_keys, unsigned long long n, int key_bytes, const KeyXform& xf, const void* splitters,
+  int num_splitters, unsigned long long* lt, unsigned long long* eq, cudaStream_t stream);
+
+} // namespace b200rs

@@ -1,0 +1,538 @@
+// Host orchestration + C ABI (include/b200rs.h).
+//
+// Replaces detail::radix_sort::dispatch / dispatch_impl::invoke / invoke_onesweep / invoke_copy
+// (/root/reference/cub/cub/device/dispatch/dispatch_radix_sort.cuh:2016-2065, :1950-2005, :1698-1948, :1364-1410)
+// and the temp-blob rule of detail::alias_temporaries (cub/cub/util_temporary_storage.cuh:49-88).
+//
+// Stream ops of one sort call:  1 memset (bins + tile counters + first look-back array)
+//                               1 upsweep histogram kernel (reads the keys once, all passes)
+//                               1 bin-scan kernel
+//                               passes x portions onesweep kernels (each zeroes the NEXT launch's look-back array)
+// No allocation, no host synchronisation, legal under stream capture.
+#include "../../include/b200rs.h"
+#include "configs.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+namespace b200rs
+{
+
+static std::atomic<int> g_config_override{-1};
+static std::atomic<unsigned long long> g_portion_override{0};
+static thread_local int t_last_launches = 0;
+
+// Optional per-op device timing (bench.py's roofline leg): when enabled, an event is recorded on the stream before
+// every op of b200rs_sort and after the last one.  Off by default; never enabled under stream capture by callers.
+constexpr int MAX_TIMED_OPS = 96;
+static thread_local bool t_timing_on = false;
+static thread_local cudaEvent_t t_events[MAX_TIMED_OPS + 1];
+static thread_local int t_event_kinds[MAX_TIMED_OPS];
+static thread_local int t_events_made = 0;
+static thread_local int t_events_used = 0;
+
+enum OpKind
+{
+  OP_MEMSET    = 0,
+  OP_HISTOGRAM = 1,
+  OP_SCAN      = 2,
+  OP_ONESWEEP  = 3,
+  OP_COPY      = 4
+};
+
+static void mark_op(cudaStream_t stream, int kind)
+{
+  t_last_launches++;
+  if (!t_timing_on || t_events_used >= MAX_TIMED_OPS)
+  {
+    return;
+  }
+  while (t_events_made <= t_events_used + 1 && t_events_made <= MAX_TIMED_OPS)
+  {
+    if (cudaEventCreate(&t_events[t_events_made]) != cudaSuccess)
+    {
+      return;
+    }
+    t_events_made++;
+  }
+  t_event_kinds[t_events_used] = kind;
+  cudaEventRecord(t_events[t_events_used], stream);
+  t_events_used++;
+}
+
+static void mark_end(cudaStream_t stream)
+{
+  if (t_timing_on && t_events_used > 0 && t_events_used < t_events_made)
+  {
+    cudaEventRecord(t_events[t_events_used], stream);
+  }
+}
+
+static const OnesweepConfig* configs_for(int key_bytes, int value_bytes, int* count)
+{
+  switch (key_bytes)
+  {
+    case 1:
+      return onesweep_configs_k1(value_bytes, count);
+    case 2:
+      return onesweep_configs_k2(value_bytes, count);
+    case 4:
+      return onesweep_configs_k4(value_bytes, count);
+    case 8:
+      return onesweep_configs_k8(value_bytes, count);
+    default:
+      *count = 0;
+      return nullptr;
+  }
+}
+
+static const OnesweepConfig* pick_config(int key_bytes, int value_bytes)
+{
+  int count                 = 0;
+  const OnesweepConfig* tab = configs_for(key_bytes, value_bytes, &count);
+  if (tab == nullptr || count == 0)
+  {
+    return nullptr;
+  }
+  int idx = g_config_override.load(std::memory_order_relaxed);
+  if (idx < 0 || idx >= count)
+  {
+    idx = 0;
+  }
+  return tab + idx;
+}
+
+static int sm_count_of_current_device(int* out)
+{
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+  if (dev >= 0 && dev < 64)
+  {
+    int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0)
+    {
+      *out = c;
+      return 0;
+    }
+  }
+  int sms = 0;
+  e       = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+  if (dev >= 0 && dev < 64)
+  {
+    cache[dev].store(sms, std::memory_order_relaxed);
+  }
+  *out = sms;
+  return 0;
+}
+
+static inline size_t align_up(size_t x, size_t a)
+{
+  return (x + a - 1) / a * a;
+}
+
+struct TempLayout
+{
+  size_t off_bins, off_ctrs, off_lb0, off_lb1, off_keys, off_vals, control_bytes, total;
+};
+
+} // namespace b200rs
+
+using namespace b200rs;
+
+extern "C" {
+
+int b200rs_version(void)
+{
+  return B200RS_VERSION;
+}
+
+int b200rs_last_launch_count(void)
+{
+  return t_last_launches;
+}
+
+int b200rs_set_config(int config_index)
+{
+  g_config_override.store(config_index, std::memory_order_relaxed);
+  return 0;
+}
+
+// diagnostic: cap the number of items one onesweep launch handles (0 = default, < 2^30) so tests can
+// exercise the multi-portion path (reference: portion_size, dispatch_radix_sort.cuh:1710-1716) at small N
+B200RS_API int b200rs_set_portion_items(unsigned long long items)
+{
+  g_portion_override.store(items, std::memory_order_relaxed);
+  return 0;
+}
+
+int b200rs_describe_config(int key_bytes, int value_bytes, int config_index, char* buf, size_t buf_len)
+{
+  int count                 = 0;
+  const OnesweepConfig* tab = configs_for(key_bytes, value_bytes, &count);
+  if (config_index < 0 || tab == nullptr)
+  {
+    return count;
+  }
+  if (config_index >= count)
+  {
+    return -1;
+  }
+  if (buf != nullptr && buf_len > 0)
+  {
+    const OnesweepConfig& c = tab[config_index];
+    snprintf(buf, buf_len, "k%dv%d threads=%d items=%d minb=%d tile=%d smem=%zu rank=%s", key_bytes, value_bytes, c.threads,
+             c.items_per_thread, c.min_blocks, c.tile_items, c.smem_bytes, c.rank_algo == 0 ? "match" : "ballot");
+  }
+  return count;
+}
+
+int b200rs_digit_histogram(
+  const void* d_keys_in,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  uint64_t* d_bins,
+  b200rs_stream_t stream_)
+{
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (key_kind < 0 || key_kind > 2 || (key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8)
+      || begin_bit < 0 || end_bit < begin_bit || end_bit > key_bytes * 8 || d_bins == nullptr
+      || (key_kind == 2 && key_bytes < 4))
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  const int passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+  if (passes == 0)
+  {
+    return 0;
+  }
+  int sms = 0;
+  if (int e = sm_count_of_current_device(&sms))
+  {
+    return e;
+  }
+  cudaError_t e = cudaMemsetAsync(d_bins, 0, size_t(passes) * RADIX * sizeof(uint64_t), stream);
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+  if (num_items == 0)
+  {
+    return 0;
+  }
+  const KeyXform xf = make_xform(key_kind, key_bytes, descending);
+  return int(launch_histogram(d_keys_in, num_items, key_bytes, reinterpret_cast<unsigned long long*>(d_bins), passes,
+                              begin_bit, end_bit, xf, sms, stream));
+}
+
+int b200rs_splitter_ranks(
+  const void* d_sorted_keys,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int descending,
+  const void* d_splitters,
+  int num_splitters,
+  uint64_t* d_lt,
+  uint64_t* d_eq,
+  b200rs_stream_t stream_)
+{
+  if (key_kind < 0 || key_kind > 2 || num_splitters < 0 || (key_kind == 2 && key_bytes < 4))
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  const KeyXform xf = make_xform(key_kind, key_bytes, descending);
+  return int(launch_splitter_ranks(d_sorted_keys, num_items, key_bytes, xf, d_splitters, num_splitters,
+                                   reinterpret_cast<unsigned long long*>(d_lt),
+                                   reinterpret_cast<unsigned long long*>(d_eq),
+                                   reinterpret_cast<cudaStream_t>(stream_)));
+}
+
+int b200rs_sort(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  int is_overwrite_okay,
+  int* selector,
+  b200rs_stream_t stream_)
+{
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  t_last_launches     = 0;
+  t_events_used       = 0;
+  if (temp_storage_bytes == nullptr || key_kind < 0 || key_kind > 2)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  if ((key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8)
+      || (value_bytes != 0 && value_bytes != 1 && value_bytes != 2 && value_bytes != 4 && value_bytes != 8
+          && value_bytes != 16)
+      || (key_kind == 2 && key_bytes < 4))
+  {
+    return int(cudaErrorNotSupported);
+  }
+  if (begin_bit < 0 || end_bit < begin_bit || end_bit > key_bytes * 8)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  const bool overwrite = is_overwrite_okay != 0;
+  const bool query     = d_temp_storage == nullptr;
+
+  // empty problem, or nothing to sort on and both buffers are the caller's scratch anyway
+  // (dispatch_radix_sort.cuh:1956-1963)
+  if (num_items == 0 || (begin_bit == end_bit && overwrite))
+  {
+    if (query)
+    {
+      *temp_storage_bytes = 1;
+    }
+    else if (selector != nullptr)
+    {
+      *selector = 0;
+    }
+    return 0;
+  }
+  if (!query)
+  {
+    if (d_keys_in == nullptr || d_keys_out == nullptr
+        || (value_bytes > 0 && (d_values_in == nullptr || d_values_out == nullptr)))
+    {
+      return int(cudaErrorInvalidValue);
+    }
+    const size_t valign = value_bytes > 8 ? 8 : size_t(value_bytes);
+    if ((reinterpret_cast<size_t>(d_keys_in) | reinterpret_cast<size_t>(d_keys_out)) % size_t(key_bytes) != 0
+        || (value_bytes > 0
+            && (reinterpret_cast<size_t>(d_values_in) | reinterpret_cast<size_t>(d_values_out)) % valign != 0))
+    {
+      return int(cudaErrorMisalignedAddress);
+    }
+  }
+
+  // pointer API with an empty bit range: plain copy (dispatch_radix_sort.cuh:1966-1977, :1364-1410)
+  if (begin_bit == end_bit)
+  {
+    if (query)
+    {
+      *temp_storage_bytes = 1;
+      return 0;
+    }
+    mark_op(stream, OP_COPY);
+    cudaError_t e = cudaMemcpyAsync(d_keys_out, d_keys_in, size_t(num_items) * key_bytes, cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess && value_bytes > 0)
+    {
+      mark_op(stream, OP_COPY);
+      e = cudaMemcpyAsync(d_values_out, d_values_in, size_t(num_items) * value_bytes, cudaMemcpyDeviceToDevice, stream);
+    }
+    mark_end(stream);
+    if (e == cudaSuccess && selector != nullptr)
+    {
+      *selector = 1;
+    }
+    return int(e);
+  }
+
+  const OnesweepConfig* cfg = pick_config(key_bytes, value_bytes);
+  if (cfg == nullptr)
+  {
+    return int(cudaErrorNotSupported);
+  }
+  const int passes          = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+  const uint64_t tile       = uint64_t(cfg->tile_items);
+  uint64_t portion_cap      = (uint64_t(1) << 30) - 1;
+  const uint64_t portion_ov = g_portion_override.load(std::memory_order_relaxed);
+  if (portion_ov != 0 && portion_ov < portion_cap)
+  {
+    portion_cap = portion_ov;
+  }
+  const uint64_t portion_items = (portion_cap / tile > 0 ? portion_cap / tile : 1) * tile;
+  const uint64_t portions      = (num_items + portion_items - 1) / portion_items;
+  const uint64_t max_tiles     = ((num_items < portion_items ? num_items : portion_items) + tile - 1) / tile;
+  const bool need_tmp          = !overwrite && passes > 1;
+
+  // temp blob: every sub-allocation 256-byte aligned, +255 so an unaligned blob can be aligned up
+  // (same rule as util_temporary_storage.cuh:49-88)
+  TempLayout L;
+  size_t off = 0;
+  L.off_bins = off;
+  off += align_up(size_t(portions) * passes * RADIX * sizeof(unsigned long long), 256);
+  L.off_ctrs = off;
+  off += align_up(size_t(portions) * passes * sizeof(uint32_t), 256);
+  L.off_lb0 = off;
+  off += align_up(size_t(max_tiles) * RADIX * sizeof(uint32_t), 256);
+  L.control_bytes = off;
+  L.off_lb1       = off;
+  off += align_up(size_t(max_tiles) * RADIX * sizeof(uint32_t), 256);
+  L.off_keys = off;
+  off += need_tmp ? align_up(size_t(num_items) * key_bytes, 256) : 0;
+  L.off_vals = off;
+  off += (need_tmp && value_bytes > 0) ? align_up(size_t(num_items) * value_bytes, 256) : 0;
+  L.total = off + 255;
+
+  if (query)
+  {
+    *temp_storage_bytes = L.total;
+    return 0;
+  }
+  if (*temp_storage_bytes < L.total)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+
+  unsigned char* base = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<size_t>(d_temp_storage), 256));
+  unsigned long long* bins = reinterpret_cast<unsigned long long*>(base + L.off_bins);
+  uint32_t* ctrs           = reinterpret_cast<uint32_t*>(base + L.off_ctrs);
+  uint32_t* lb[2]          = {reinterpret_cast<uint32_t*>(base + L.off_lb0), reinterpret_cast<uint32_t*>(base + L.off_lb1)};
+  void* keys_tmp           = need_tmp ? base + L.off_keys : nullptr;
+  void* vals_tmp           = (need_tmp && value_bytes > 0) ? base + L.off_vals : nullptr;
+
+  int sms = 0;
+  if (int e = sm_count_of_current_device(&sms))
+  {
+    return e;
+  }
+  const KeyXform xf = make_xform(key_kind, key_bytes, descending);
+
+  mark_op(stream, OP_MEMSET);
+  cudaError_t e = cudaMemsetAsync(base, 0, L.control_bytes, stream);
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+  // upsweep over the whole input: counts land in portion 0's bins, then become exclusive offsets
+  mark_op(stream, OP_HISTOGRAM);
+  e = launch_histogram(d_keys_in, num_items, key_bytes, bins, passes, begin_bit, end_bit, xf, sms, stream);
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+  mark_op(stream, OP_SCAN);
+  e = launch_scan_bins(bins, passes, stream);
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+
+  const uint64_t launches = uint64_t(passes) * portions;
+  uint64_t launch_idx     = 0;
+  const void* src_k       = d_keys_in;
+  const void* src_v       = d_values_in;
+  for (int pass = 0; pass < passes; ++pass)
+  {
+    void* dst_k;
+    void* dst_v;
+    if (overwrite)
+    {
+      // ping-pong between the caller's two buffers
+      dst_k = (pass % 2 == 0) ? d_keys_out : const_cast<void*>(d_keys_in);
+      dst_v = (pass % 2 == 0) ? d_values_out : const_cast<void*>(d_values_in);
+    }
+    else
+    {
+      // never write buffer 0; the last pass must land in buffer 1 (dispatch_radix_sort.cuh:1850-1857, :1935-1942)
+      const bool to_out = ((passes - 1 - pass) % 2) == 0;
+      dst_k             = to_out ? d_keys_out : keys_tmp;
+      dst_v             = to_out ? d_values_out : vals_tmp;
+    }
+    const int bit   = begin_bit + pass * RADIX_BITS;
+    const int nbits = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
+    for (uint64_t portion = 0; portion < portions; ++portion, ++launch_idx)
+    {
+      const uint64_t first = portion * portion_items;
+      const uint64_t count = (num_items - first) < portion_items ? (num_items - first) : portion_items;
+      const unsigned tiles = unsigned((count + tile - 1) / tile);
+      PassArgs a;
+      a.keys_in       = static_cast<const unsigned char*>(src_k) + first * key_bytes;
+      a.keys_out      = dst_k;
+      a.vals_in       = value_bytes > 0 ? static_cast<const unsigned char*>(src_v) + first * value_bytes : nullptr;
+      a.vals_out      = value_bytes > 0 ? dst_v : nullptr;
+      a.lookback      = lb[launch_idx & 1];
+      a.lookback_next = nullptr;
+      a.lookback_next_tiles = 0;
+      if (launch_idx + 1 < launches)
+      {
+        const uint64_t nportion = (portion + 1 < portions) ? portion + 1 : 0;
+        const uint64_t nfirst   = nportion * portion_items;
+        const uint64_t ncount   = (num_items - nfirst) < portion_items ? (num_items - nfirst) : portion_items;
+        a.lookback_next         = lb[(launch_idx + 1) & 1];
+        a.lookback_next_tiles   = uint32_t((ncount + tile - 1) / tile);
+      }
+      a.tile_counter = ctrs + (portion * passes + pass);
+      a.bins         = bins + (portion * passes + pass) * RADIX;
+      a.bins_next    = (portion + 1 < portions) ? bins + ((portion + 1) * passes + pass) * RADIX : nullptr;
+      a.num_items    = uint32_t(count);
+      a.shift        = bit;
+      a.mask         = (1u << nbits) - 1u;
+      a.first_pass   = pass == 0;
+      a.last_pass    = pass == passes - 1;
+      a.xf           = xf;
+      mark_op(stream, OP_ONESWEEP);
+      e = cfg->launch(a, tiles, stream);
+      if (e != cudaSuccess)
+      {
+        return int(e);
+      }
+    }
+    src_k = dst_k;
+    src_v = dst_v;
+  }
+  mark_end(stream);
+  if (selector != nullptr)
+  {
+    *selector = overwrite ? (passes & 1) : 1;
+  }
+  return 0;
+}
+
+int b200rs_timing_enable(int on)
+{
+  t_timing_on   = on != 0;
+  t_events_used = 0;
+  return 0;
+}
+
+int b200rs_timing_read(int* kinds, float* ms, int capacity)
+{
+  const int n = t_events_used;
+  if (n == 0)
+  {
+    return 0;
+  }
+  cudaError_t e = cudaEventSynchronize(t_events[n]);
+  if (e != cudaSuccess)
+  {
+    return -int(e);
+  }
+  int written = 0;
+  for (int i = 0; i < n && written < capacity; ++i, ++written)
+  {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, t_events[i], t_events[i + 1]);
+    kinds[written] = t_event_kinds[i];
+    ms[written]    = t;
+  }
+  return written;
+}
+
+} // extern "C"

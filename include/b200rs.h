@@ -1,0 +1,170 @@
+/*
+ * b200rs.h -- C ABI of the B200-native (sm_100a) LSD radix sort: the drop-in boundary for the
+ * reference's cub::DeviceRadixSort hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and returns a cudaError_t value
+ * as int (0 == cudaSuccess).  The model is the reference's own C ABI for this path,
+ *   cccl_device_radix_sort(build, d_temp_storage, temp_storage_bytes, keys_in, keys_out, values_in,
+ *                          values_out, decomposer, num_items, begin_bit, end_bit, is_overwrite_okay,
+ *                          selector, stream)
+ *   (/root/reference/c/parallel/include/cccl/c/radix_sort.h:110-124, impl c/parallel/src/radix_sort.cu:582-661),
+ * minus the NVRTC "build" object (kernels here are compiled ahead of time) and with the iterator structs
+ * replaced by (pointer, key kind, key bytes, value bytes).  The C++ templates cub::DeviceRadixSort /
+ * cub::DoubleBuffer (include/cub/device/device_radix_sort.cuh in this repo) and the thrust::sort shim
+ * (include/thrust/sort.h) are header-only wrappers that type-erase to these calls.
+ *
+ * Conventions (same as cub/cub/device/device_radix_sort.cuh:300-317, dispatch_radix_sort.cuh:1739-1743,
+ * :1950-1977, util_temporary_storage.cuh:75-78 in the reference):
+ *   - two-phase: d_temp_storage == NULL  => only *temp_storage_bytes is written, no work is enqueued;
+ *     otherwise *temp_storage_bytes is the size of the blob provided, too small => cudaErrorInvalidValue (1);
+ *   - all work is enqueued on `stream` and is NOT synchronised; no allocation, no host sync; legal under
+ *     CUDA stream capture;
+ *   - the caller owns every buffer; keys/values ranges must not overlap each other or the temp blob;
+ *   - never throws, never prints.
+ */
+#ifndef B200RS_H_
+#define B200RS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#  define B200RS_API __declspec(dllexport)
+#else
+#  define B200RS_API __attribute__((visibility("default")))
+#endif
+
+/* Opaque CUDA stream (cudaStream_t / CUstream); NULL is the legacy default stream. */
+typedef struct CUstream_st* b200rs_stream_t;
+
+/* How the key bits are mapped to an order-preserving unsigned integer ("twiddle"):
+ * cub::Traits<T>::TwiddleIn/Out, /root/reference/cub/cub/util_type.cuh:857-865 (unsigned),
+ * :906-914 (signed), :953-963 (floating point). */
+typedef enum b200rs_key_kind
+{
+  B200RS_KEY_UINT  = 0, /* unsigned integers, bool, char: identity            */
+  B200RS_KEY_INT   = 1, /* two's complement signed: flip the sign bit         */
+  B200RS_KEY_FLOAT = 2  /* IEEE-754: negative -> ~x, else flip the sign bit;  */
+                        /* -0.0 and +0.0 compare equal (stable), NaNs by bits */
+} b200rs_key_kind;
+
+#define B200RS_VERSION 100 /* 0.1.0 */
+
+/* Library version (B200RS_VERSION of the build). */
+B200RS_API int b200rs_version(void);
+
+/*
+ * Device-wide stable LSD radix sort of `num_items` keys (and, if value_bytes > 0, the values that travel
+ * with them) on bits [begin_bit, end_bit) of the transformed key.
+ *
+ * Replaces: cub::DeviceRadixSort::{SortKeys,SortKeysDescending,SortPairs,SortPairsDescending}, pointer and
+ * DoubleBuffer overloads (/root/reference/cub/cub/device/device_radix_sort.cuh:412,1127,1776,2295,3034,3644,
+ * 4211,4669) == detail::radix_sort::dispatch (dispatch/dispatch_radix_sort.cuh:2016-2065).
+ *
+ *   d_keys_in / d_keys_out      "buffer 0" / "buffer 1" of the key DoubleBuffer (device pointers)
+ *   d_values_in / d_values_out  same for values; ignored when value_bytes == 0
+ *   key_kind                    b200rs_key_kind
+ *   key_bytes                   1, 2, 4 or 8
+ *   value_bytes                 0 (keys only), 1, 2, 4, 8 or 16; pointers must be aligned to
+ *                               min(value_bytes, 8)
+ *   begin_bit, end_bit          0 <= begin_bit <= end_bit <= 8*key_bytes
+ *   descending                  0 ascending, 1 descending (equal keys keep INPUT order in both)
+ *   is_overwrite_okay           0: pointer API -- buffer 0 is never written, the result is in buffer 1,
+ *                                  *selector = 1, temp blob holds ~N*(key_bytes+value_bytes) extra;
+ *                               1: DoubleBuffer API -- both buffers are clobbered, *selector (0/1) tells
+ *                                  which one holds the result, temp blob is O(N/tile)
+ *   selector                    host pointer, written by every successful EXECUTE call (untouched by the size
+ *                               query; may be NULL)
+ *
+ * Returns 0 (cudaSuccess), 1 (cudaErrorInvalidValue: bad arguments or temp blob too small),
+ * 801 (cudaErrorNotSupported: unsupported key/value width) or the CUDA error of a failed launch.
+ */
+B200RS_API int b200rs_sort(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  int is_overwrite_okay,
+  int* selector,
+  b200rs_stream_t stream);
+
+/*
+ * The upsweep on its own: one read of the keys produces the digit histogram of every 8-bit pass.
+ * d_bins is a device array of uint64[ceil((end_bit-begin_bit)/8) * 256], overwritten.
+ *
+ * Replaces: DeviceRadixSortHistogramKernel / AgentRadixSortHistogram::Process
+ * (/root/reference/cub/cub/device/dispatch/kernels/kernel_radix_sort.cuh:447-473,
+ *  cub/cub/agent/agent_radix_sort_histogram.cuh:248-279).  Exposed so the kernel can be checked and timed alone.
+ */
+B200RS_API int b200rs_digit_histogram(
+  const void* d_keys_in,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  uint64_t* d_bins,
+  b200rs_stream_t stream);
+
+/*
+ * Multi-GPU support kernel: for a locally SORTED key array, count for each of
+ * `num_splitters` splitter keys how many local keys order strictly before it (d_lt[i]) and how many are
+ * equal to it (d_eq[i]) under the same transform/order as b200rs_sort with the full bit range.
+ * d_splitters: device array of `num_splitters` keys (same type as the keys).  d_lt/d_eq: device uint64 arrays.
+ *
+ * Replaces the per-probe local counts of the reference's multi-GPU sort
+ * (/root/reference/cudax/include/cuda/experimental/__multi_gpu/algorithm/sort/hss/histogramming.h:522-610).
+ */
+B200RS_API int b200rs_splitter_ranks(
+  const void* d_sorted_keys,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int descending,
+  const void* d_splitters,
+  int num_splitters,
+  uint64_t* d_lt,
+  uint64_t* d_eq,
+  b200rs_stream_t stream);
+
+/* Number of kernel launches / async ops the last b200rs_sort call on this host thread enqueued
+ * (bench.py's `gpu_launches`).  Thread-local. */
+B200RS_API int b200rs_last_launch_count(void);
+
+/* Per-op device timing for the calling host thread (bench.py's roofline leg).  While enabled, b200rs_sort records a
+ * CUDA event on `stream` before each op it enqueues and one after the last.  b200rs_timing_read waits for the last
+ * sort call of this thread and returns how many ops it wrote: kinds[i] in {0 memset, 1 upsweep histogram, 2 bin scan,
+ * 3 onesweep pass, 4 copy}, ms[i] = device milliseconds between consecutive events.  Do not enable under capture. */
+B200RS_API int b200rs_timing_enable(int on);
+B200RS_API int b200rs_timing_read(int* kinds, float* ms, int capacity);
+
+/* Tuning/diagnostic override: force the onesweep tile configuration index for subsequent calls from this
+ * process (-1 = automatic).  Used only by tools/sweep and tests; not part of the drop-in surface. */
+B200RS_API int b200rs_set_config(int config_index);
+
+/* Diagnostic: cap the number of items one onesweep launch handles (0 = default, < 2^30) so tests can exercise the
+ * multi-portion path (reference: portion_size, dispatch_radix_sort.cuh:1710-1716) at small N. */
+B200RS_API int b200rs_set_portion_items(unsigned long long items);
+
+/* Human-readable description of configuration `config_index` for (key_bytes, value_bytes); returns the number of
+ * configurations available when config_index < 0.  buf may be NULL. */
+B200RS_API int b200rs_describe_config(int key_bytes, int value_bytes, int config_index, char* buf, size_t buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RS_H_ */

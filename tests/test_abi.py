@@ -1,0 +1,94 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/b200rs.h declares,
+and its argument checking / size query (which touch no GPU) behave like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from cccl_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200rs.h")).read()
+    return sorted(set(re.findall(r"B200RS_API\s+\w[\w\s\*]*?\b(b200rs_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(_native.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.b200rs_version() == 100
+
+
+def _query(n, kb, vb, begin, end, overwrite, kind=0):
+    return _native.sort_raw(0, 0, 0, 0, 0, 0, n, kind, kb, vb, begin, end, False, overwrite)
+
+
+def test_size_query_is_pure_and_deterministic():
+    # dispatch_radix_sort.cuh:1739-1743 -- no device work on the query; runs here without a GPU
+    a, sel = _query(1 << 20, 4, 0, 0, 32, False)
+    b, _ = _query(1 << 20, 4, 0, 0, 32, False)
+    assert a == b and sel == -1
+    c, _ = _query(1 << 20, 4, 0, 0, 32, True)
+    assert a - c >= (1 << 20) * 4  # pointer API carries an extra key buffer (device_radix_sort.cuh:310-315)
+    d, _ = _query(1 << 20, 4, 4, 0, 32, False)
+    assert d - a >= (1 << 20) * 4 - 4096
+    one_pass, _ = _query(1 << 20, 4, 0, 0, 8, False)
+    assert one_pass < (1 << 20)  # single pass goes straight from in to out
+
+
+def test_empty_problem_needs_one_byte():
+    # dispatch_radix_sort.cuh:1956-1962
+    assert _query(0, 4, 0, 0, 32, False)[0] == 1
+    assert _query(1000, 4, 0, 8, 8, True)[0] == 1
+    assert _query(1000, 4, 0, 8, 8, False)[0] == 1
+
+
+@pytest.mark.parametrize("args,code", [
+    ((10, 3, 0, 0, 24, False), 801),    # unsupported key width
+    ((10, 4, 3, 0, 32, False), 801),    # unsupported value width
+    ((10, 4, 0, 8, 40, False), 1),      # end_bit beyond the key
+    ((10, 4, 0, 9, 8, False), 1),       # begin > end
+    ((10, 2, 0, 0, 16, False, 2), 801), # 16-bit float keys
+])
+def test_bad_arguments(args, code):
+    with pytest.raises(_native.B200RSError) as e:
+        _query(*args)
+    assert e.value.code == code
+
+
+def test_too_small_temp_is_invalid_value():
+    # util_temporary_storage.cuh:75-78.  The size check comes before any device access, so fake pointers are fine.
+    need, _ = _query(100000, 4, 0, 0, 32, True)
+    with pytest.raises(_native.B200RSError) as e:
+        _native.sort_raw(0x1000, need - 1, 0x10000, 0x20000, 0, 0, 100000, 0, 4, 0, 0, 32, False, True)
+    assert e.value.code == 1
+
+
+def test_config_tables_described():
+    for kb in (1, 2, 4, 8):
+        for vb in (0, 1, 2, 4, 8, 16):
+            d = _native.describe_configs(kb, vb)
+            assert len(d) >= 1 and f"k{kb}v{vb}" in d[0]
+
+
+def test_product_does_not_touch_the_oracle():
+    """The oracle is test infrastructure: nothing shipped may import, load or link it."""
+    bad = []
+    for base in ("cccl_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            if os.sep + "build" in dirpath:
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", "Makefile")):
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"liboracle|oracle_lib|oracle/|ref_thrust", txt):
+                        bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

@@ -1,0 +1,350 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI against the oracle on the
+same seeded inputs, bit-exact, plus size-independent properties at BASELINE.json's full sizes.
+
+Case list mirrors cub/test/catch2_test_device_radix_sort_keys.cu (:75-113 sizes x order, :115-161 bit windows,
+:165-219 +-0, :221-283 NaN, :287-340 entropy, :342-374 all-equal, :418-447 DoubleBuffer) and ..._pairs.cu
+(:29 value widths, :81-86 stability, :89-131 DoubleBuffer)."""
+import numpy as np
+import pytest
+import torch
+
+from gen import V16, make_keys, make_values
+from gpu_util import assert_same_bits, gpu_histogram, gpu_sort
+from oracle_lib import oracle_histogram, oracle_sort
+
+pytestmark = pytest.mark.gpu
+
+KEY_DTYPES = [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.uint64, np.int64, np.float64]
+
+
+def check_keys(k, **kw):
+    got, info = gpu_sort(k, **kw)
+    okw = {x: kw[x] for x in ("descending", "begin_bit", "end_bit") if x in kw}
+    assert_same_bits(got, oracle_sort(k, **okw), f"keys {k.dtype} n={k.size} {kw}")
+    return info
+
+
+def check_pairs(k, v, **kw):
+    gk, gv, info = gpu_sort(k, v, **kw)
+    okw = {x: kw[x] for x in ("descending", "begin_bit", "end_bit") if x in kw}
+    ok, ov = oracle_sort(k, v, **okw)
+    assert_same_bits(gk, ok, f"pair keys {k.dtype}/{v.dtype} n={k.size} {kw}")
+    assert_same_bits(gv, ov, f"pair values (stability) {k.dtype}/{v.dtype} n={k.size} {kw}")
+    return info
+
+
+def test_golden_vectors_on_gpu():
+    k = np.array([8, 6, 7, 5, 3, 0, 9], dtype=np.int32)
+    v = np.arange(7, dtype=np.int32)
+    gk, gv, _ = gpu_sort(k, v)
+    assert gk.tolist() == [0, 3, 5, 6, 7, 8, 9] and gv.tolist() == [5, 4, 3, 1, 2, 0, 6]
+    gk, gv, _ = gpu_sort(k, v, descending=True)
+    assert gk.tolist() == [9, 8, 7, 6, 5, 3, 0] and gv.tolist() == [6, 0, 2, 1, 3, 4, 5]
+    k = np.array([1, 3, 6, 5, 2, 0, 4], dtype=np.int32)
+    gk, gv, _ = gpu_sort(k, v, api="double")
+    assert gk.tolist() == [0, 1, 2, 3, 4, 5, 6] and gv.tolist() == [5, 0, 4, 1, 6, 3, 2]
+
+
+def test_committed_golden_fixtures_on_gpu():
+    import glob
+    import os
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+    assert files
+    for f in files:
+        z = np.load(f)
+        kw = dict(descending=bool(z["descending"]), begin_bit=int(z["begin_bit"]), end_bit=int(z["end_bit"]))
+        if "vals_in" in z:
+            gk, gv, _ = gpu_sort(z["keys_in"], z["vals_in"], **kw)
+            assert_same_bits(gk, z["keys_out"], f)
+            assert_same_bits(gv, z["vals_out"], f)
+        else:
+            gk, _ = gpu_sort(z["keys_in"], **kw)
+            assert_same_bits(gk, z["keys_out"], f)
+
+
+@pytest.mark.parametrize("dtype", KEY_DTYPES)
+@pytest.mark.parametrize("descending", [False, True])
+def test_keys_all_types_sizes(dtype, descending):
+    rng = np.random.default_rng(11)
+    sizes = [0, 1, 2, 31, 32, 33, 255, 4095, 4096, 4097, 8191, 8192, 8193, 12289, 100_003]
+    sizes += rng.integers(32, 1 << 20, size=3).tolist()
+    for n in sizes:
+        check_keys(make_keys("uniform", n, dtype, seed=n + 1), descending=descending)
+
+
+@pytest.mark.parametrize("dtype", [np.uint32, np.uint64, np.float32, np.int64, np.uint16, np.uint8])
+def test_bit_windows(dtype):
+    bits = np.dtype(dtype).itemsize * 8
+    cuts = sorted({0, bits // 3, 3 * bits // 4, bits})
+    k = make_keys("uniform", 70_001, dtype, seed=9)
+    v = make_values(k.size, np.uint32)
+    for b in cuts:
+        for e in cuts:
+            if b <= e:
+                for desc in (False, True):
+                    check_pairs(k, v, begin_bit=b, end_bit=e, descending=desc)
+    check_keys(k, begin_bit=3, end_bit=4)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_signed_zeros_and_nans(dtype):
+    udt = np.uint32 if dtype == np.float32 else np.uint64
+    n = 50_000
+    rng = np.random.default_rng(2)
+    k = rng.standard_normal(n).astype(dtype)
+    k[rng.integers(0, n, n // 5)] = 0.0
+    k[rng.integers(0, n, n // 5)] = -0.0
+    nanbits = make_keys("uniform", n // 10, dtype, seed=4).view(udt)
+    expmask = udt(0x7F800000) if dtype == np.float32 else udt(0x7FF0000000000000)
+    idx = rng.integers(0, n, n // 10)
+    k.view(udt)[idx] = nanbits | expmask | udt(1)  # +-NaN with random payloads
+    k[rng.integers(0, n, 100)] = np.inf
+    k[rng.integers(0, n, 100)] = -np.inf
+    v = make_values(n, np.uint32)
+    for desc in (False, True):
+        check_pairs(k, v, descending=desc)
+        check_pairs(k, v, descending=desc, api="double")
+        check_pairs(k, v, descending=desc, begin_bit=5, end_bit=np.dtype(dtype).itemsize * 8 - 1)
+
+
+@pytest.mark.parametrize("dist", ["entropy2", "entropy3", "entropy5", "equal", "few2", "few16", "few256", "sorted",
+                                  "reverse"])
+@pytest.mark.parametrize("dtype", [np.uint32, np.uint64])
+def test_skewed_distributions_pairs_stable(dist, dtype):
+    n = 300_007
+    k = make_keys(dist, n, dtype, seed=21)
+    v = make_values(n, np.uint32)
+    check_pairs(k, v)
+    check_pairs(k, v, descending=True, api="double")
+
+
+@pytest.mark.parametrize("vdtype", [np.uint8, np.uint16, np.uint32, np.uint64, V16])
+@pytest.mark.parametrize("kdtype", [np.uint8, np.uint16, np.uint32, np.uint64])
+def test_value_widths(kdtype, vdtype):
+    for n in (1, 777, 40_000):
+        k = make_keys("few256" if n > 1000 else "uniform", n, kdtype, seed=n)
+        v = make_values(n, vdtype)
+        check_pairs(k, v)
+        check_pairs(k, v, api="double", descending=True)
+
+
+def test_double_buffer_selector_and_pass_parity():
+    # result is wherever selector says (catch2_test_device_radix_sort_keys.cu:441-446)
+    k = make_keys("uniform", 50_000, np.uint32, seed=8)
+    for e, want_sel in ((8, 1), (16, 0), (24, 1), (32, 0)):
+        info = check_keys(k, begin_bit=0, end_bit=e, api="double")
+        assert info["selector"] == want_sel
+    info = check_keys(k, begin_bit=8, end_bit=8, api="double")
+    assert info["selector"] == 0 and info["temp_bytes"] == 1
+    info = check_keys(k, begin_bit=8, end_bit=8, api="pointer")  # pointer API: plain copy
+    assert info["selector"] == 1
+
+
+def test_unaligned_temp_storage_and_streams():
+    k = make_keys("uniform", 123_457, np.uint32, seed=1)
+    v = make_values(k.size, np.uint64)
+    check_pairs(k, v, temp_misalign=3)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        check_pairs(k, v, stream=s)
+
+
+def test_multi_portion_path():
+    """Forces tiny portions so several launches per pass chain through bins_next
+    (reference: portion loop, dispatch_radix_sort.cuh:1859-1933; large-N tests ..._keys.cu:488-519)."""
+    from cccl_b200 import _native
+
+    lib = _native.lib()
+    try:
+        lib.b200rs_set_portion_items(20_000)
+        for dtype in (np.uint32, np.uint64):
+            k = make_keys("entropy3", 131_072 + 77, dtype, seed=5)
+            v = make_values(k.size, np.uint32)
+            info = check_pairs(k, v)
+            assert info["launches"] > 3 + np.dtype(dtype).itemsize
+            check_pairs(k, v, api="double", descending=True)
+    finally:
+        lib.b200rs_set_portion_items(0)
+
+
+def test_every_compiled_config_is_correct():
+    from cccl_b200 import _native
+
+    lib = _native.lib()
+    try:
+        for kdt, vdt in ((np.uint32, None), (np.uint32, np.uint32), (np.uint64, None), (np.uint64, np.uint32)):
+            n_cfg = len(_native.describe_configs(np.dtype(kdt).itemsize, np.dtype(vdt).itemsize if vdt else 0))
+            k = make_keys("entropy2", 200_003, kdt, seed=77)
+            for c in range(n_cfg):
+                lib.b200rs_set_config(c)
+                if vdt is None:
+                    check_keys(k)
+                else:
+                    check_pairs(k, make_values(k.size, vdt))
+    finally:
+        lib.b200rs_set_config(-1)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64, np.float32])
+def test_upsweep_histogram_alone(dtype):
+    for n, off in ((0, 0), (5, 1), (100_003, 0), (100_003, 3), (1 << 20, 1)):
+        k = make_keys("entropy2", n, dtype, seed=3)
+        for desc in (False, True):
+            got = gpu_histogram(k, descending=desc, offset_items=off)
+            want = oracle_histogram(k, descending=desc)
+            assert np.array_equal(got, want), (dtype, n, off, desc)
+    k = make_keys("uniform", 50_000, dtype, seed=3)
+    bits = np.dtype(dtype).itemsize * 8
+    got = gpu_histogram(k, begin_bit=bits // 3, end_bit=bits - 1)
+    assert np.array_equal(got, oracle_histogram(k, begin_bit=bits // 3, end_bit=bits - 1))
+
+
+def test_cuda_graph_capture():
+    """The execute call is allocation-free and stream-ordered: legal under capture
+    (cub/test/catch2_test_launch_helper.h:91-121)."""
+    from cccl_b200 import _native
+    from gpu_util import to_dev, to_host
+
+    k = make_keys("uniform", 300_000, np.uint32, seed=6)
+    d_in, d_out = to_dev(k), to_dev(np.zeros_like(k))
+    need, _ = _native.sort_raw(0, 0, d_in.data_ptr(), d_out.data_ptr(), 0, 0, k.size, 0, 4, 0, 0, 32, False, False)
+    temp = torch.empty(need, dtype=torch.uint8, device="cuda")
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            _native.sort_raw(temp.data_ptr(), need, d_in.data_ptr(), d_out.data_ptr(), 0, 0, k.size, 0, 4, 0, 0, 32,
+                             False, False, s.cuda_stream)
+    for seed in (6, 7):
+        k = make_keys("uniform", 300_000, np.uint32, seed=seed)
+        d_in.copy_(to_dev(k))
+        g.replay()
+        torch.cuda.synchronize()
+        assert_same_bits(to_host(d_out, np.uint32, k.size), np.sort(k), "graph replay")
+
+
+def test_python_mirror_api():
+    from cccl_b200 import DoubleBuffer, SortOrder, make_radix_sort, radix_sort
+
+    h_k = np.array([-5, 4, 2, -3, 2, 4, 0, -1, 2, 8], dtype=np.int32)
+    h_v = np.arange(10, dtype=np.float32)
+    d_k, d_v = torch.from_numpy(h_k).cuda(), torch.from_numpy(h_v).cuda()
+    o_k, o_v = torch.empty_like(d_k), torch.empty_like(d_v)
+    radix_sort(d_in_keys=d_k, d_out_keys=o_k, d_in_values=d_v, d_out_values=o_v, num_items=10,
+               order=SortOrder.ASCENDING)
+    torch.cuda.synchronize()
+    order = np.argsort(h_k, kind="stable")
+    assert o_k.cpu().numpy().tolist() == h_k[order].tolist() and o_v.cpu().numpy().tolist() == h_v[order].tolist()
+    kb, vb = DoubleBuffer(d_k, o_k), DoubleBuffer(d_v, o_v)
+    sorter = make_radix_sort(d_in_keys=kb, d_out_keys=None, d_in_values=vb, d_out_values=None,
+                             order=SortOrder.DESCENDING)
+    kw = dict(d_in_keys=kb, d_out_keys=None, d_in_values=vb, d_out_values=None, num_items=10)
+    nbytes = sorter(temp_storage=None, **kw)
+    temp = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    sorter(temp_storage=temp, **kw)
+    torch.cuda.synchronize()
+    order = np.argsort(-h_k.astype(np.int64), kind="stable")
+    assert kb.current().cpu().numpy().tolist() == h_k[order].tolist()
+    assert vb.current().cpu().numpy().tolist() == h_v[order].tolist()
+    assert kb.selector == vb.selector
+
+
+def _checksum(t: torch.Tensor):
+    return int(t.view(torch.int64).sum().item()) if t.numel() % 1 == 0 else 0
+
+
+@pytest.mark.parametrize("case", ["u32_keys", "u64_u32_pairs_uniform", "u64_u32_pairs_entropy5", "f32_desc_window",
+                                  "i64_desc_window"])
+def test_full_size_properties(case):
+    """BASELINE.json sizes (2^28): sortedness under the sort's own order, multiset preservation (order-independent
+    checksums), value stability (equal-key runs carry increasing original indices), key/value pairing."""
+    n = 1 << 28
+    g = torch.Generator(device="cuda").manual_seed(5)
+
+    def rnd64(count):
+        return torch.randint(-(2**63), 2**63 - 1, (count,), dtype=torch.int64, device="cuda", generator=g)
+
+    from cccl_b200 import _native
+
+    if case == "u32_keys":
+        keys = rnd64(n // 2).view(torch.int32)  # raw bits of n u32 keys
+        kind, kb, vb, desc, b, e = 0, 4, 0, False, 0, 32
+    elif case.startswith("u64_u32_pairs"):
+        keys = rnd64(n)
+        if case.endswith("entropy5"):
+            for _ in range(4):
+                keys &= rnd64(n)
+        kind, kb, vb, desc, b, e = 0, 8, 4, False, 0, 64
+    elif case == "f32_desc_window":
+        keys = rnd64(n // 2).view(torch.int32)
+        kind, kb, vb, desc, b, e = 2, 4, 0, True, 8, 24
+    else:
+        keys = rnd64(n)
+        kind, kb, vb, desc, b, e = 1, 8, 0, True, 16, 48
+    out = torch.empty_like(keys)
+    vals = torch.arange(n, dtype=torch.int32, device="cuda") if vb else None
+    vout = torch.empty_like(vals) if vb else None
+    p = lambda t: t.data_ptr() if t is not None else 0
+    need, _ = _native.sort_raw(0, 0, p(keys), p(out), p(vals), p(vout), n, kind, kb, vb, b, e, desc, False)
+    temp = torch.empty(need, dtype=torch.uint8, device="cuda")
+    _, sel = _native.sort_raw(temp.data_ptr(), need, p(keys), p(out), p(vals), p(vout), n, kind, kb, vb, b, e, desc,
+                              False)
+    torch.cuda.synchronize()
+    assert sel == 1
+    del temp
+
+    # order key: the transformed, window-masked key as a signed-comparable int64 (computed with torch on device;
+    # this is the CHECK, not the product)
+    def order_key(t):
+        if kb == 4:
+            u = t.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+            if kind == 2:
+                neg = (u >> 31) == 1
+                u = torch.where(u == 0x80000000, torch.zeros_like(u), u)  # -0 -> +0
+                neg = (u >> 31) == 1
+                u = torch.where(neg, (~u) & 0xFFFFFFFF, u ^ 0x80000000)
+            w = (u >> b) & ((1 << (e - b)) - 1)
+            return w
+        u = t.view(torch.int64)
+        if kind == 1:
+            u = u ^ (-(2**63))
+        # unsigned 64-bit window -> keep as int64 after shifting so it compares correctly
+        if e - b < 64:
+            w = (u >> b) & ((1 << (e - b)) - 1)
+            return w
+        return u ^ (-(2**63))  # unsigned order as signed order
+
+    chunk = 1 << 26
+    prev_last = None
+    for s in range(0, n, chunk):
+        ok = order_key(out[s:s + chunk])
+        d = ok[1:] - ok[:-1] if (e - b) < 63 else None
+        if desc:
+            good = ok[1:] <= ok[:-1]
+        else:
+            good = ok[1:] >= ok[:-1]
+        assert bool(good.all()), f"{case}: not sorted in chunk at {s}"
+        if vb:
+            same = ok[1:] == ok[:-1]
+            vv = vout[s:s + chunk].to(torch.int64)
+            assert bool((~same | (vv[1:] > vv[:-1])).all()), f"{case}: stability broken in chunk at {s}"
+        if prev_last is not None:
+            assert (ok[0] <= prev_last) if desc else (ok[0] >= prev_last)
+        prev_last = ok[-1]
+        del ok, good
+    # multiset preserved: sum and xor-like checksums of raw bits are order independent
+    a64, b64 = keys.view(torch.int64), out.view(torch.int64)
+    if kb == 8:
+        assert int(a64.sum()) == int(b64.sum())
+        assert int((a64 * a64).sum()) == int((b64 * b64).sum())
+    else:
+        a32, b32 = keys.view(torch.int32).to(torch.int64), out.view(torch.int32).to(torch.int64)
+        assert int(a32.sum()) == int(b32.sum())
+        assert int((a32 * a32).sum()) == int((b32 * b32).sum())
+        del a32, b32
+    if vb:
+        # pairing: out[i] must equal keys[vout[i]]
+        for s in range(0, n, chunk):
+            idx = vout[s:s + chunk].to(torch.int64)
+            assert bool((keys.view(torch.int64)[idx] == out.view(torch.int64)[s:s + chunk]).all())
