@@ -21,6 +21,7 @@ EXPORTS = (
     "b200rs_last_launch_count",
     "b200rs_set_config",
     "b200rs_set_portion_items",
+    "b200rs_set_force_big",
     "b200rs_describe_config",
     "b200rs_timing_enable",
     "b200rs_timing_read",
@@ -61,6 +62,8 @@ def lib() -> ctypes.CDLL:
         l.b200rs_set_config.argtypes = [i32]
         l.b200rs_set_portion_items.restype = i32
         l.b200rs_set_portion_items.argtypes = [ctypes.c_ulonglong]
+        l.b200rs_set_force_big.restype = i32
+        l.b200rs_set_force_big.argtypes = [i32]
         l.b200rs_describe_config.restype = i32
         l.b200rs_describe_config.argtypes = [i32, i32, i32, ctypes.c_char_p, ctypes.c_size_t]
         l.b200rs_timing_enable.restype = i32

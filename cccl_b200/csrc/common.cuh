@@ -100,9 +100,12 @@ inline KeyXform make_xform(int key_kind, int key_bytes, int descending)
   x.desc_mask  = descending ? all : 0;
   if (key_kind == 2)
   {
-    // twiddle_in(-0.0 = high) = ~high ; twiddle_in(+0.0 = 0) = high ; then descending inverts both
-    x.neg_zero = ((~high) & all) ^ x.desc_mask;
-    x.pos_zero = high ^ x.desc_mask;
+    // Exactly the reference's rule (radix_rank_sort_operations.cuh:44-82): in the kernel's key domain (after the
+    // descending inversion) the pattern TwiddleIn(-0.0) = 0x7f..f is ranked as TwiddleIn(+0.0) = 0x80..0.  For
+    // ascending sorts that maps -0.0 onto +0.0; for descending sorts the inverted +0.0 IS 0x7f..f and is mapped
+    // onto the inverted -0.0.  Either way both zeros share one digit view, so they tie and keep input order.
+    x.neg_zero = (~high) & all;
+    x.pos_zero = high;
   }
   else
   {
@@ -198,6 +201,7 @@ struct PassArgs
   uint32_t mask;           // (1 << digit_bits) - 1
   int first_pass;          // transform on load
   int last_pass;           // inverse transform on store
+  int big;                 // whole array has >= 2^32 items: 64-bit output offsets
   KeyXform xf;
 };
 

@@ -21,6 +21,7 @@ namespace b200rs
 
 static std::atomic<int> g_config_override{-1};
 static std::atomic<unsigned long long> g_portion_override{0};
+static std::atomic<bool> g_force_big{false};
 static thread_local int t_last_launches = 0;
 
 // Optional per-op device timing (bench.py's roofline leg): when enabled, an event is recorded on the stream before
@@ -172,6 +173,14 @@ int b200rs_set_config(int config_index)
 B200RS_API int b200rs_set_portion_items(unsigned long long items)
 {
   g_portion_override.store(items, std::memory_order_relaxed);
+  return 0;
+}
+
+// diagnostic: force the 64-bit-offset kernels (normally only used for arrays of >= 2^32 items) so tests can
+// exercise them at small N
+B200RS_API int b200rs_set_force_big(int on)
+{
+  g_force_big.store(on != 0, std::memory_order_relaxed);
   return 0;
 }
 
@@ -486,6 +495,7 @@ int b200rs_sort(
       a.mask         = (1u << nbits) - 1u;
       a.first_pass   = pass == 0;
       a.last_pass    = pass == passes - 1;
+      a.big          = (num_items >> 32) != 0 || g_force_big.load(std::memory_order_relaxed);
       a.xf           = xf;
       mark_op(stream, OP_ONESWEEP);
       e = cfg->launch(a, tiles, stream);

@@ -1,19 +1,32 @@
-// onesweep instantiations for 2-byte keys
+// onesweep instantiations for 2-byte keys.  Index 0 of each table is the default configuration.
 #include "inst.cuh"
 
 namespace b200rs
 {
 using K = uint16_t;
+#define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
 
-static const OnesweepConfig cfg_v0[]  = {make_config<K, 0, 512, 16, RANK_MATCH>()};
-static const OnesweepConfig cfg_v1[]  = {make_config<K, 1, 512, 16, RANK_MATCH>()};
-static const OnesweepConfig cfg_v2[]  = {make_config<K, 2, 512, 16, RANK_MATCH>()};
-static const OnesweepConfig cfg_v4[]  = {make_config<K, 4, 512, 16, RANK_MATCH>()};
-static const OnesweepConfig cfg_v8[]  = {make_config<K, 8, 512, 12, RANK_MATCH>()};
-static const OnesweepConfig cfg_v16[] = {make_config<K, 16, 512, 8, RANK_MATCH>()};
+static const OnesweepConfig cfg_v0[] = {
+  C(0, 512, 16, 2)
+};
+static const OnesweepConfig cfg_v1[] = {
+  C(1, 512, 16, 2)
+};
+static const OnesweepConfig cfg_v2[] = {
+  C(2, 512, 16, 2)
+};
+static const OnesweepConfig cfg_v4[] = {
+  C(4, 512, 16, 2)
+};
+static const OnesweepConfig cfg_v8[] = {
+  C(8, 512, 12, 2)
+};
+static const OnesweepConfig cfg_v16[] = {
+  C(16, 512, 8, 2)
+};
 
-#define B200RS_TABLE(arr)                            \
-  *count = int(sizeof(arr) / sizeof(arr[0]));        \
+#define B200RS_TABLE(arr)                     \
+  *count = int(sizeof(arr) / sizeof(arr[0])); \
   return arr
 
 const OnesweepConfig* onesweep_configs_k2(int value_bytes, int* count)

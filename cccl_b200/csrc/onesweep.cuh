@@ -5,16 +5,24 @@
 //  cub/cub/agent/agent_radix_sort_onesweep.cuh:152-739) and the ranking it calls
 // (cub/cub/block/block_radix_rank.cuh:913-1213).  Same contract seen from outside: keys_out/vals_out
 // receive the items of keys_in/vals_in stably partitioned by the digit (key >> shift) & mask, starting at
-// the per-digit global offsets in `bins`.  The inside is a different design:
+// the per-digit global offsets in `bins`.  The inside is a different design, driven by the ncu finding that
+// on B200 this kernel is ISSUE-SLOT and shared-memory-wavefront bound, not HBM bound (profiles/r1_*):
+// everything is about instructions and shared-memory transactions per key.
 //
 //   * no "early counts" histogram pre-pass over the tile: the warp-private running offsets that ranking
-//     maintains ARE the per-warp digit histograms once the last item is ranked, so every key costs one
-//     match + one shared load + (leader only) one shared store;
-//   * ranking with MATCH.ANY (one instruction) instead of an 8-ballot loop (template switch keeps the
-//     ballot variant for measurement);
-//   * the chained scan status words of the NEXT pass are zeroed by this pass (no memset between passes);
-//   * keys stay bit-ordered in HBM between passes (transform fused into first load / last store);
-//   * 64-bit per-digit output bases in shared memory, so one launch addresses arrays beyond 2^32 items.
+//     maintains ARE the per-warp digit histograms once the last item is ranked (saves one shared atomic
+//     per key);
+//   * match-by-ballot written so each digit bit costs ~3 SASS instructions (VOTE, predicated NOT, AND; the
+//     eight predicates come from one R2P + one LOP3.P); MATCH.ANY is kept as a template switch for measurement
+//     only -- it runs at ~1 per 40 cycles per SM on B200 and loses by 1.6x;
+//   * the highest peer lane is the leader, so ONE POPC per key gives both the lane's rank among its peers
+//     and (for the leader) the group size;
+//   * shared memory is addressed with explicit 32-bit shared-window addresses (one LEA per access);
+//   * per-digit output offsets in shared memory are 32-bit element offsets (one LDS.32 + IADD3 + IMAD.WIDE +
+//     STG per key); a BIG variant with 64-bit offsets serves arrays of 2^32 items and more;
+//   * float -0.0 handling is compiled in only for floating-point keys;
+//   * the chained scan status words of the NEXT launch are zeroed by this one (no memset between passes);
+//   * keys stay bit-ordered in HBM between passes (transform fused into first load / last store).
 //
 // Stable order inside a tile: warp w owns the contiguous chunk [w*32*IPT, (w+1)*32*IPT); its item i of
 // lane l is element i*32+l of the chunk (each load instruction covers one contiguous 32-key run, fully
@@ -38,136 +46,237 @@ struct OnesweepSmem
   static constexpr int NW          = NT / 32;
   static constexpr int TILE        = NT * IPT;
   static constexpr int ITEM_BYTES  = int(sizeof(U)) > VBYTES ? int(sizeof(U)) : VBYTES;
-  static constexpr size_t OFF_WARP = 0;                                        // u32 [NW][256]
-  static constexpr size_t OFF_GOFF = OFF_WARP + size_t(NW) * RADIX * 4;        // u64 [256]
-  static constexpr size_t OFF_MISC = OFF_GOFF + size_t(RADIX) * 8;             // u32 [16]
-  static constexpr size_t OFF_DATA = OFF_MISC + 64;                            // staged tile
-  static constexpr size_t BYTES    = OFF_DATA + size_t(TILE) * ITEM_BYTES;
+  static constexpr uint32_t OFF_WARP = 0;                             // u32 [NW][256] running offsets
+  static constexpr uint32_t OFF_GOFF = OFF_WARP + NW * RADIX * 4;     // u64 [256] per-digit output offsets
+  static constexpr uint32_t OFF_MISC = OFF_GOFF + RADIX * 8;          // u32 [16]
+  static constexpr uint32_t OFF_DATA = OFF_MISC + 64;                 // staged tile (16-byte aligned)
+  static constexpr size_t BYTES      = size_t(OFF_DATA) + size_t(TILE) * ITEM_BYTES;
 };
 
-template <class U, int VBYTES, int NT, int IPT, int RANK, int MINB>
-__global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
+__device__ __forceinline__ uint32_t lanemask_gt()
+{
+  uint32_t r;
+  asm("mov.u32 %0, %%lanemask_gt;" : "=r"(r));
+  return r;
+}
+
+// ---- shared memory through 32-bit shared-window addresses.  "memory" clobbers keep the compiler from moving
+// these across each other; within a converged warp the LSU executes them in program order.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds64(uint32_t addr)
+{
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, unsigned long long v)
+{
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+template <class T>
+__device__ __forceinline__ T lds_t(uint32_t addr)
+{
+  T v;
+  if (sizeof(T) == 1)
+  {
+    uint32_t t;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t) : "r"(addr) : "memory");
+    v = *reinterpret_cast<T*>(&t);
+  }
+  else if (sizeof(T) == 2)
+  {
+    uint16_t t;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(t) : "r"(addr) : "memory");
+    v = *reinterpret_cast<T*>(&t);
+  }
+  else if (sizeof(T) == 4)
+  {
+    uint32_t t = lds32(addr);
+    v          = *reinterpret_cast<T*>(&t);
+  }
+  else if (sizeof(T) == 8)
+  {
+    unsigned long long t = lds64(addr);
+    v                    = *reinterpret_cast<T*>(&t);
+  }
+  else
+  {
+    unsigned long long t[2] = {lds64(addr), lds64(addr + 8)};
+    v                       = *reinterpret_cast<T*>(t);
+  }
+  return v;
+}
+template <class T>
+__device__ __forceinline__ void sts_t(uint32_t addr, T v)
+{
+  if (sizeof(T) == 1)
+  {
+    uint32_t t = *reinterpret_cast<uint8_t*>(&v);
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(t) : "memory");
+  }
+  else if (sizeof(T) == 2)
+  {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<uint16_t*>(&v)) : "memory");
+  }
+  else if (sizeof(T) == 4)
+  {
+    sts32(addr, *reinterpret_cast<uint32_t*>(&v));
+  }
+  else if (sizeof(T) == 8)
+  {
+    sts64(addr, *reinterpret_cast<unsigned long long*>(&v));
+  }
+  else
+  {
+    const unsigned long long* t = reinterpret_cast<const unsigned long long*>(&v);
+    sts64(addr, t[0]);
+    sts64(addr + 8, t[1]);
+  }
+}
+
+// lanes of the warp whose 8-bit digit equals this lane's: per bit {predicate, ballot, flip for lanes whose bit is
+// clear, and}.  Bits above the pass's digit width are zero in every lane and cost nothing in correctness.
+__device__ __forceinline__ uint32_t match_digit_ballot(uint32_t d)
+{
+  uint32_t peers;
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    ".reg .b32 v, t;\n"
+    "and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; @!p not.b32 %0, %0;\n"
+    "and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+    "and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+    "and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+    "and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+    "and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+    "and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+    "and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+    "}\n"
+    : "=&r"(peers)
+    : "r"(d));
+  return peers;
+}
+
+template <int N>
+__device__ __forceinline__ void put16(uint32_t (&pk)[N], int i, uint32_t v)
+{
+  pk[i / 2] = (i & 1) ? __byte_perm(pk[i / 2], v, 0x5410) : v; // v < 65536; the even half initialises the pair
+}
+template <int N>
+__device__ __forceinline__ void update16(uint32_t (&pk)[N], int i, uint32_t v)
+{
+  pk[i / 2] = __byte_perm(pk[i / 2], v, (i & 1) ? 0x5410 : 0x3254); // replace one half, keep the other
+}
+template <int N>
+__device__ __forceinline__ uint32_t get16(const uint32_t (&pk)[N], int i)
+{
+  return (i & 1) ? (pk[i / 2] >> 16) : (pk[i / 2] & 0xffffu);
+}
+
+template <bool FLOATK, class U>
+__device__ __forceinline__ uint32_t pass_digit(U key, int shift, uint32_t mask, U neg_zero, U pos_zero)
+{
+  if (FLOATK)
+  {
+    key = key == neg_zero ? pos_zero : key; // -0.0 ranks as +0.0; the stored bits are untouched
+  }
+  return uint32_t(key >> shift) & mask;
+}
+
+// The tile body.  FULL: every item of the tile is valid (all tiles but possibly the last one of a portion).
+template <class U, int VBYTES, int NT, int IPT, int RANK, bool FLOATK, bool BIG, bool FULL>
+__device__ __forceinline__ void onesweep_tile(
+  const PassArgs& a, const uint32_t sbase, const uint32_t tile, const uint32_t tile_base, const uint32_t valid)
 {
   using L = OnesweepSmem<U, VBYTES, NT, IPT>;
   using V = typename value_of<VBYTES>::type;
-  constexpr int NW   = L::NW;
-  constexpr int TILE = L::TILE;
-  static_assert(NT >= RADIX && NT % 32 == 0, "one thread per digit is required");
+  constexpr int NW = L::NW;
 
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t* warp_off        = reinterpret_cast<uint32_t*>(smem + L::OFF_WARP);
-  unsigned long long* goff  = reinterpret_cast<unsigned long long*>(smem + L::OFF_GOFF);
-  uint32_t* misc            = reinterpret_cast<uint32_t*>(smem + L::OFF_MISC);
-  U* skeys                  = reinterpret_cast<U*>(smem + L::OFF_DATA);
-  V* svals                  = reinterpret_cast<V*>(smem + L::OFF_DATA);
-
-  const XformT<U> xf(a.xf);
-  const uint32_t tid  = threadIdx.x;
-  const uint32_t lane = tid & 31;
-  const uint32_t warp = tid >> 5;
-  const int shift     = a.shift;
+  const uint32_t tid   = threadIdx.x;
+  const uint32_t lane  = tid & 31;
+  const uint32_t warp  = tid >> 5;
+  const int shift      = a.shift;
   const uint32_t dmask = a.mask;
-
-  // ---- dynamic tile id: a tile only starts after all its predecessors started (look-back cannot deadlock)
-  if (tid == 0)
-  {
-    misc[8] = atomicAdd(a.tile_counter, 1u);
-  }
-  uint32_t* my_off = warp_off + warp * RADIX;
-#pragma unroll
-  for (int j = 0; j < RADIX / 32; ++j)
-  {
-    my_off[j * 32 + lane] = 0;
-  }
-  __syncthreads();
-  const uint32_t tile      = misc[8];
-  const uint32_t tile_base = tile * uint32_t(TILE);
-  const uint32_t valid     = min(uint32_t(TILE), a.num_items - tile_base);
-  const bool full          = valid == uint32_t(TILE);
+  const U neg_zero     = U(a.xf.neg_zero);
+  const U pos_zero     = U(a.xf.pos_zero);
+  const uint32_t s_warp = sbase + L::OFF_WARP;
+  const uint32_t s_goff = sbase + L::OFF_GOFF;
+  const uint32_t s_misc = sbase + L::OFF_MISC;
+  const uint32_t s_data = sbase + L::OFF_DATA;
+  const uint32_t s_mine = s_warp + warp * (RADIX * 4); // this warp's running offsets
 
   // ---- load keys, warp-striped
   U key[IPT];
   const uint32_t chunk = warp * 32 * IPT + lane;
   {
     const U* kin = static_cast<const U*>(a.keys_in) + tile_base + chunk;
-    if (full)
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
     {
+      key[i] = (FULL || chunk + i * 32 < valid) ? kin[i * 32] : U(0);
+    }
+    if (a.first_pass)
+    {
+      const XformT<U> xf(a.xf);
 #pragma unroll
       for (int i = 0; i < IPT; ++i)
       {
-        key[i] = kin[i * 32];
-      }
-      if (a.first_pass)
-      {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i)
-        {
-          key[i] = twiddle_in(key[i], xf);
-        }
+        key[i] = twiddle_in(key[i], xf);
       }
     }
-    else
+    if (!FULL)
     {
 #pragma unroll
       for (int i = 0; i < IPT; ++i)
       {
-        const bool ok = chunk + i * 32 < valid;
-        U k           = ok ? kin[i * 32] : U(0);
-        if (a.first_pass)
+        if (chunk + i * 32 >= valid)
         {
-          k = twiddle_in(k, xf);
+          key[i] = U(~U(0)); // padding ranks last: max digit, last in tile order
         }
-        key[i] = ok ? k : U(~U(0)); // padding ranks last: max digit, last in tile order
       }
     }
   }
 
-  // ---- rank: warp-private running digit offsets
-  uint32_t rank[IPT];
+  // ---- rank: warp-private running digit offsets; afterwards the warp's row holds its digit histogram
+  // staged positions, two 16-bit values per register.  Besides halving the registers, the PRMT packing stops ptxas
+  // from keeping BOTH addends of every rank alive (it otherwise fuses the add into the later IADD3 and spills).
+  uint32_t rank2[(IPT + 1) / 2];
   const uint32_t lt_mask = lanemask_lt();
+  const uint32_t gt_mask = lanemask_gt();
 #pragma unroll
   for (int i = 0; i < IPT; ++i)
   {
-    const uint32_t d = digit_of(digit_view(key[i], xf), shift, dmask);
-    uint32_t peers;
-    if (RANK == RANK_MATCH)
-    {
-      peers = __match_any_sync(0xffffffffu, d);
-    }
-    else
-    {
-      peers = 0xffffffffu;
-#pragma unroll
-      for (int b = 0; b < RADIX_BITS; ++b)
-      {
-        const bool bit      = (d >> b) & 1;
-        const uint32_t vote = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? vote : ~vote;
-      }
-    }
+    const uint32_t d      = pass_digit<FLOATK>(key[i], shift, dmask, neg_zero, pos_zero);
+    const uint32_t peers  = (RANK == RANK_MATCH) ? __match_any_sync(0xffffffffu, d) : match_digit_ballot(d);
     const uint32_t before = __popc(peers & lt_mask);
-    const uint32_t off    = my_off[d];
-    __syncwarp();
-    if (before == 0)
+    const uint32_t ctr    = s_mine + d * 4;
+    const uint32_t off    = lds32(ctr);
+    if ((peers & gt_mask) == 0) // highest peer lane: its `before` + 1 is the group size
     {
-      my_off[d] = off + __popc(peers);
+      sts32(ctr, off + before + 1);
     }
-    __syncwarp();
-    rank[i] = off + before;
+    put16(rank2, i, off + before);
   }
   __syncthreads();
 
   // ---- per-digit tile totals (one thread per digit), publish, block-wide exclusive scan over digits
   uint32_t total = 0, excl = 0;
-  uint32_t wcount[NW];
   uint32_t* lb_word = a.lookback + size_t(tile) * RADIX + tid;
   if (tid < RADIX)
   {
 #pragma unroll
     for (int w = 0; w < NW; ++w)
     {
-      wcount[w] = warp_off[w * RADIX + tid];
-      total += wcount[w];
+      total += lds32(s_warp + (w * RADIX + tid) * 4);
     }
     st_relaxed_u32(lb_word, (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | total);
     uint32_t incl = total;
@@ -182,7 +291,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
     }
     if (lane == 31)
     {
-      misc[warp] = incl;
+      sts32(s_misc + warp * 4, incl);
     }
     excl = incl - total;
   }
@@ -192,14 +301,17 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
 #pragma unroll
     for (int w = 0; w < RADIX / 32; ++w)
     {
-      excl += (uint32_t(w) < warp) ? misc[w] : 0u;
+      const uint32_t ws = lds32(s_misc + w * 4);
+      excl += (uint32_t(w) < warp) ? ws : 0u;
     }
     uint32_t run = excl;
 #pragma unroll
     for (int w = 0; w < NW; ++w)
     {
-      warp_off[w * RADIX + tid] = run;
-      run += wcount[w];
+      const uint32_t addr = s_warp + (w * RADIX + tid) * 4;
+      const uint32_t c    = lds32(addr);
+      sts32(addr, run);
+      run += c;
     }
   }
   __syncthreads();
@@ -208,9 +320,13 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
 #pragma unroll
   for (int i = 0; i < IPT; ++i)
   {
-    const uint32_t d = digit_of(digit_view(key[i], xf), shift, dmask);
-    rank[i] += my_off[d];
-    skeys[rank[i]] = key[i];
+    const uint32_t d = pass_digit<FLOATK>(key[i], shift, dmask, neg_zero, pos_zero);
+    const uint32_t r = get16(rank2, i) + lds32(s_mine + d * 4);
+    if (VBYTES > 0)
+    {
+      update16(rank2, i, r);
+    }
+    sts_t<U>(s_data + r * uint32_t(sizeof(U)), key[i]);
   }
 
   // values are fetched now so their latency hides behind the look-back
@@ -221,7 +337,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
     {
-      if (full || chunk + i * 32 < valid)
+      if (FULL || chunk + i * 32 < valid)
       {
         val[i] = vin[i * 32];
       }
@@ -252,7 +368,15 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
       st_relaxed_u32(lb_word, LB_INCLUSIVE | (prefix + total));
     }
     const unsigned long long gbase = a.bins[tid] + prefix;
-    goff[tid]                      = gbase - excl;
+    // element offset such that out[off + staged position] is the output slot (wraps consistently when negative)
+    if (BIG)
+    {
+      sts64(s_goff + tid * 8, gbase - excl);
+    }
+    else
+    {
+      sts32(s_goff + tid * 4, uint32_t(gbase) - excl);
+    }
     if (a.bins_next != nullptr && tile_base + valid == a.num_items)
     {
       a.bins_next[tid] = gbase + total;
@@ -270,25 +394,45 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
   // ---- coalesced scatter: consecutive threads write consecutive staged positions
   uint32_t digs[(IPT + 3) / 4];
   U* kout = static_cast<U*>(a.keys_out);
+  auto store_keys = [&](auto last_tag) {
+    constexpr bool LAST = decltype(last_tag)::value;
+    const XformT<U> xf(a.xf);
 #pragma unroll
-  for (int i = 0; i < IPT; ++i)
-  {
-    const uint32_t pos = i * NT + tid;
-    uint32_t d         = 0;
-    if (full || pos < valid)
+    for (int i = 0; i < IPT; ++i)
     {
-      const U k = skeys[pos];
-      d         = digit_of(digit_view(k, xf), shift, dmask);
-      kout[goff[d] + pos] = a.last_pass ? twiddle_out(k, xf) : k;
-    }
-    if (VBYTES > 0)
-    {
-      if ((i & 3) == 0)
+      const uint32_t pos = i * NT + tid;
+      uint32_t d         = 0;
+      if (FULL || pos < valid)
       {
-        digs[i / 4] = 0;
+        const U k = lds_t<U>(s_data + pos * uint32_t(sizeof(U)));
+        d         = pass_digit<FLOATK>(k, shift, dmask, neg_zero, pos_zero);
+        const U o = LAST ? twiddle_out(k, xf) : k;
+        if (BIG)
+        {
+          kout[lds64(s_goff + d * 8) + pos] = o;
+        }
+        else
+        {
+          kout[lds32(s_goff + d * 4) + pos] = o;
+        }
       }
-      digs[i / 4] |= d << (8 * (i & 3));
+      if (VBYTES > 0)
+      {
+        if ((i & 3) == 0)
+        {
+          digs[i / 4] = 0;
+        }
+        digs[i / 4] |= d << (8 * (i & 3));
+      }
     }
+  };
+  if (a.last_pass)
+  {
+    store_keys(std::true_type{});
+  }
+  else
+  {
+    store_keys(std::false_type{});
   }
 
   if (VBYTES > 0)
@@ -297,9 +441,9 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
     {
-      if (full || chunk + i * 32 < valid)
+      if (FULL || chunk + i * 32 < valid)
       {
-        svals[rank[i]] = val[i];
+        sts_t<V>(s_data + get16(rank2, i) * uint32_t(sizeof(V)), val[i]);
       }
     }
     __syncthreads();
@@ -308,12 +452,59 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
     for (int i = 0; i < IPT; ++i)
     {
       const uint32_t pos = i * NT + tid;
-      if (full || pos < valid)
+      if (FULL || pos < valid)
       {
-        const uint32_t d    = (digs[i / 4] >> (8 * (i & 3))) & 0xffu;
-        vout[goff[d] + pos] = svals[pos];
+        const uint32_t d = (digs[i / 4] >> (8 * (i & 3))) & 0xffu;
+        const V v        = lds_t<V>(s_data + pos * uint32_t(sizeof(V)));
+        if (BIG)
+        {
+          vout[lds64(s_goff + d * 8) + pos] = v;
+        }
+        else
+        {
+          vout[lds32(s_goff + d * 4) + pos] = v;
+        }
       }
     }
+  }
+}
+
+template <class U, int VBYTES, int NT, int IPT, int RANK, int MINB, bool FLOATK, bool BIG>
+__global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
+{
+  using L = OnesweepSmem<U, VBYTES, NT, IPT>;
+  constexpr int TILE = L::TILE;
+  static_assert(NT >= RADIX && NT % 32 == 0, "one thread per digit is required");
+  static_assert(TILE <= 65536, "staged positions are kept in 16 bits");
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
+  const uint32_t tid   = threadIdx.x;
+
+  // ---- dynamic tile id: a tile only starts after all its predecessors started (look-back cannot deadlock)
+  if (tid == 0)
+  {
+    sts32(sbase + L::OFF_MISC + 32, atomicAdd(a.tile_counter, 1u));
+  }
+  {
+    const uint32_t row = sbase + L::OFF_WARP + (tid >> 5) * (RADIX * 4) + (tid & 31) * 4;
+#pragma unroll
+    for (int j = 0; j < RADIX / 32; ++j)
+    {
+      sts32(row + j * 128, 0);
+    }
+  }
+  __syncthreads();
+  const uint32_t tile      = lds32(sbase + L::OFF_MISC + 32);
+  const uint32_t tile_base = tile * uint32_t(TILE);
+  const uint32_t valid     = min(uint32_t(TILE), a.num_items - tile_base);
+  if (valid == uint32_t(TILE))
+  {
+    onesweep_tile<U, VBYTES, NT, IPT, RANK, FLOATK, BIG, true>(a, sbase, tile, tile_base, valid);
+  }
+  else
+  {
+    onesweep_tile<U, VBYTES, NT, IPT, RANK, FLOATK, BIG, false>(a, sbase, tile, tile_base, valid);
   }
 }
 

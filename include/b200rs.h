@@ -160,6 +160,10 @@ B200RS_API int b200rs_set_config(int config_index);
  * multi-portion path (reference: portion_size, dispatch_radix_sort.cuh:1710-1716) at small N. */
 B200RS_API int b200rs_set_portion_items(unsigned long long items);
 
+/* Diagnostic: force the 64-bit-offset kernel variants (normally selected only for arrays of >= 2^32 items, the
+ * reference's 64-bit OffsetT case, detail/choose_offset.cuh:35-52) so tests can exercise them at small N. */
+B200RS_API int b200rs_set_force_big(int on);
+
 /* Human-readable description of configuration `config_index` for (key_bytes, value_bytes); returns the number of
  * configurations available when config_index < 0.  buf may be NULL. */
 B200RS_API int b200rs_describe_config(int key_bytes, int value_bytes, int config_index, char* buf, size_t buf_len);

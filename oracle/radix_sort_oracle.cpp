@@ -12,7 +12,8 @@
 //
 // What is restated (reference file:line, all relative to /root/reference):
 //   * get_striped_keys        cub/test/catch2_radix_sort_helper.cuh:174-214
-//       bit-cast -> (float: -0 -> +0) -> Traits<T>::TwiddleIn -> mask to [begin_bit,end_bit)
+//       bit-cast -> Traits<T>::TwiddleIn -> (descending: ~) -> (float: pattern of -0 -> pattern of +0, the
+//       device rule of radix_rank_sort_operations.cuh:44-82) -> mask to [begin_bit,end_bit)
 //   * Traits<T>::TwiddleIn    cub/cub/util_type.cuh:857-865 (unsigned: identity),
 //                             :906-914 (signed: flip sign bit),
 //                             :953-963 (float: negative -> ~x, else flip sign bit)
@@ -58,9 +59,14 @@ U twiddle_in(U bits, int kind)
   }
 }
 
-// catch2_radix_sort_helper.cuh:174-214
+// catch2_radix_sort_helper.cuh:174-214, with the float-zero rule taken from the DEVICE code it models
+// (radix_rank_sort_operations.cuh:44-82): the key is twiddled, then (descending) inverted, and in THAT domain the
+// pattern TwiddleIn(-0.0) = 0x7f..f is replaced by TwiddleIn(+0.0) = 0x80..0 before the digit bits are taken.
+// For a full-width sort this is indistinguishable from the helper's "-0 -> +0 before twiddling"; for a descending
+// sort on a partial bit window the two differ in where the zeros land, and the real cub::DeviceRadixSort output
+// (pinned on the B200 by tests/test_vs_reference_gpu.py and tests/golden/cub_*.npz) is what this follows.
 template <class U>
-std::vector<U> striped_keys(const U* keys, uint64_t n, int kind, int begin_bit, int end_bit)
+std::vector<U> striped_keys(const U* keys, uint64_t n, int kind, int begin_bit, int end_bit, bool descending)
 {
   constexpr int total_bits = int(sizeof(U) * 8);
   constexpr U high         = U(1) << (total_bits - 1);
@@ -68,12 +74,15 @@ std::vector<U> striped_keys(const U* keys, uint64_t n, int kind, int begin_bit, 
   const int num_bits = end_bit - begin_bit;
   for (uint64_t i = 0; i < n; ++i)
   {
-    U key = keys[i];
-    if (kind == KIND_FLOAT && key == high)
+    U key = twiddle_in(keys[i], kind);
+    if (descending)
     {
-      key = 0; // -0.0 compares equal to +0.0
+      key = U(~key); // radix_rank_sort_operations.cuh:545-552
     }
-    key = twiddle_in(key, kind);
+    if (kind == KIND_FLOAT && key == U(~high))
+    {
+      key = high; // ProcessFloatMinusZero, radix_rank_sort_operations.cuh:69-82
+    }
     if (begin_bit > 0 || end_bit < total_bits)
     {
       // ((1 << num_bits) - 1) << begin_bit, written so num_bits == total_bits cannot overflow
@@ -85,26 +94,19 @@ std::vector<U> striped_keys(const U* keys, uint64_t n, int kind, int begin_bit, 
   return out;
 }
 
-// catch2_radix_sort_helper.cuh:238-268
+// catch2_radix_sort_helper.cuh:238-268.  The keys above are already inverted for descending sorts, so one ascending
+// stable sort serves both directions (equivalent to the helper's '>' on the un-inverted keys: inversion reverses
+// the order of distinct window values and keeps ties, which the stable sort leaves in input order).
 template <class U>
 std::vector<uint64_t> permutation(const U* keys, uint64_t n, int kind, int begin_bit, int end_bit, bool descending)
 {
-  std::vector<U> sk = striped_keys(keys, n, kind, begin_bit, end_bit);
+  std::vector<U> sk = striped_keys(keys, n, kind, begin_bit, end_bit, descending);
   std::vector<uint64_t> perm(n);
   std::iota(perm.begin(), perm.end(), uint64_t(0));
   const U* p = sk.data();
-  if (descending)
-  {
-    std::stable_sort(perm.begin(), perm.end(), [p](uint64_t a, uint64_t b) {
-      return p[a] > p[b];
-    });
-  }
-  else
-  {
-    std::stable_sort(perm.begin(), perm.end(), [p](uint64_t a, uint64_t b) {
-      return p[a] < p[b];
-    });
-  }
+  std::stable_sort(perm.begin(), perm.end(), [p](uint64_t a, uint64_t b) {
+    return p[a] < p[b];
+  });
   return perm;
 }
 
@@ -152,15 +154,14 @@ int hist_impl(const void* keys_in, uint64_t n, int kind, int begin_bit, int end_
   std::fill(bins, bins + uint64_t(passes) * 256, uint64_t(0));
   for (uint64_t i = 0; i < n; ++i)
   {
-    U key = kin[i];
-    if (kind == KIND_FLOAT && key == high)
-    {
-      key = 0;
-    }
-    key = twiddle_in(key, kind);
+    U key = twiddle_in(kin[i], kind);
     if (descending)
     {
       key = U(~key);
+    }
+    if (kind == KIND_FLOAT && key == U(~high))
+    {
+      key = high;
     }
     for (int p = 0; p < passes; ++p)
     {
