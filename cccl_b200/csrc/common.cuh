@@ -89,7 +89,21 @@ __host__ __device__ __forceinline__ uint32_t digit_of(U view, int shift, uint32_
   return uint32_t(view >> shift) & mask;
 }
 
-inline KeyXform make_xform(int key_kind, int key_bytes, int descending)
+// Largest N the reference sorts with its single-CTA kernel on sm_100 (dispatch_radix_sort.cuh:1980; policy
+// tuning_radix_sort.cuh:1747,1833-1841 scaled by util_arch.cuh:128-138): 4864 / 2304 / 1024 items for a dominant
+// item size of <=4 / 8 / 16 bytes.  Only used to pick the reference's float-zero rule (see make_xform).
+inline unsigned long long reference_single_tile_items(int key_bytes, int value_bytes)
+{
+  int dom = key_bytes > value_bytes ? key_bytes : value_bytes;
+  dom     = dom < 4 ? 4 : dom;
+  int items = 19 * 4 / dom;
+  items     = items < 1 ? 1 : items;
+  int threads = (48 * 1024 / (dom * items) + 31) / 32 * 32;
+  threads     = threads > 256 ? 256 : threads;
+  return (unsigned long long) threads * (unsigned long long) items;
+}
+
+inline KeyXform make_xform(int key_kind, int key_bytes, int descending, bool single_tile_rule = false)
 {
   const int bits                 = key_bytes * 8;
   const unsigned long long all   = bits == 64 ? ~0ull : ((1ull << bits) - 1);
@@ -106,6 +120,16 @@ inline KeyXform make_xform(int key_kind, int key_bytes, int descending)
     // onto the inverted -0.0.  Either way both zeros share one digit view, so they tie and keep input order.
     x.neg_zero = (~high) & all;
     x.pos_zero = high;
+    // The reference's single-CTA kernel (small N) does not invert keys for descending sorts; it maps -0.0 onto +0.0
+    // in the un-inverted domain (radix_rank_sort_operations.cuh:44-55 "all other sorting implementations").  In the
+    // inverted domain this kernel works in, that is the opposite replacement.  Only observable for descending sorts
+    // on a partial bit window; callers pass single_tile_rule = (N <= reference_single_tile_items) to stay bit-exact
+    // with the reference at every N.
+    if (descending && single_tile_rule)
+    {
+      x.neg_zero = high;
+      x.pos_zero = (~high) & all;
+    }
   }
   else
   {

@@ -421,7 +421,8 @@ int b200rs_sort(
   {
     return e;
   }
-  const KeyXform xf = make_xform(key_kind, key_bytes, descending);
+  const KeyXform xf =
+    make_xform(key_kind, key_bytes, descending, num_items <= reference_single_tile_items(key_bytes, value_bytes));
 
   mark_op(stream, OP_MEMSET);
   cudaError_t e = cudaMemsetAsync(base, 0, L.control_bytes, stream);

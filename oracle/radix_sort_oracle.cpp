@@ -59,14 +59,31 @@ U twiddle_in(U bits, int kind)
   }
 }
 
+// Largest N the reference sorts with its single-CTA kernel on sm_100 (dispatch_radix_sort.cuh:1980):
+// single_tile policy = scale_reg_bound(256 threads, 19 items, max(key, value size))
+// (tuning_radix_sort.cuh:1747,1833-1841; util_arch.cuh:128-138) => 4864 / 2304 / 1024 items for a dominant item
+// size of <=4 / 8 / 16 bytes.
+inline uint64_t reference_single_tile_items(int key_bytes, int value_bytes)
+{
+  const int dom     = std::max(4, std::max(key_bytes, value_bytes));
+  const int items   = std::max(1, 19 * 4 / dom);
+  const int threads = std::min(256, (48 * 1024 / (dom * items) + 31) / 32 * 32);
+  return uint64_t(threads) * uint64_t(items);
+}
+
 // catch2_radix_sort_helper.cuh:174-214, with the float-zero rule taken from the DEVICE code it models
-// (radix_rank_sort_operations.cuh:44-82): the key is twiddled, then (descending) inverted, and in THAT domain the
-// pattern TwiddleIn(-0.0) = 0x7f..f is replaced by TwiddleIn(+0.0) = 0x80..0 before the digit bits are taken.
-// For a full-width sort this is indistinguishable from the helper's "-0 -> +0 before twiddling"; for a descending
-// sort on a partial bit window the two differ in where the zeros land, and the real cub::DeviceRadixSort output
-// (pinned on the B200 by tests/test_vs_reference_gpu.py and tests/golden/cub_*.npz) is what this follows.
+// (radix_rank_sort_operations.cuh:44-82).  The reference has TWO device rules and which one runs depends on N:
+//   * onesweep (N above the single-tile size): the key is twiddled, then (descending) inverted, and in THAT domain
+//     the pattern TwiddleIn(-0.0) = 0x7f..f is replaced by TwiddleIn(+0.0) = 0x80..0 before the digit bits are taken;
+//   * single-tile kernel (N <= reference_single_tile_items; BlockRadixSort handles descending by reversing digits,
+//     not by inverting keys): the replacement happens in the NON-inverted domain, which is exactly the helper's
+//     "-0 -> +0 before twiddling".
+// For a full-width sort the two are indistinguishable; for a descending sort on a partial bit window they differ in
+// where the zeros land.  The real cub::DeviceRadixSort outputs pin both: tests/golden/cub_*.npz (small N, single
+// tile; large N, onesweep) and tests/test_vs_reference_gpu.py on the B200.
 template <class U>
-std::vector<U> striped_keys(const U* keys, uint64_t n, int kind, int begin_bit, int end_bit, bool descending)
+std::vector<U> striped_keys(
+  const U* keys, uint64_t n, int kind, int begin_bit, int end_bit, bool descending, bool single_tile_rule)
 {
   constexpr int total_bits = int(sizeof(U) * 8);
   constexpr U high         = U(1) << (total_bits - 1);
@@ -75,13 +92,17 @@ std::vector<U> striped_keys(const U* keys, uint64_t n, int kind, int begin_bit, 
   for (uint64_t i = 0; i < n; ++i)
   {
     U key = twiddle_in(keys[i], kind);
+    if (kind == KIND_FLOAT && single_tile_rule && key == U(~high))
+    {
+      key = high; // ProcessFloatMinusZero on the un-inverted key (block_radix_sort path)
+    }
     if (descending)
     {
       key = U(~key); // radix_rank_sort_operations.cuh:545-552
     }
-    if (kind == KIND_FLOAT && key == U(~high))
+    if (kind == KIND_FLOAT && !single_tile_rule && key == U(~high))
     {
-      key = high; // ProcessFloatMinusZero, radix_rank_sort_operations.cuh:69-82
+      key = high; // ProcessFloatMinusZero, radix_rank_sort_operations.cuh:69-82 (onesweep path)
     }
     if (begin_bit > 0 || end_bit < total_bits)
     {
@@ -98,9 +119,10 @@ std::vector<U> striped_keys(const U* keys, uint64_t n, int kind, int begin_bit, 
 // stable sort serves both directions (equivalent to the helper's '>' on the un-inverted keys: inversion reverses
 // the order of distinct window values and keeps ties, which the stable sort leaves in input order).
 template <class U>
-std::vector<uint64_t> permutation(const U* keys, uint64_t n, int kind, int begin_bit, int end_bit, bool descending)
+std::vector<uint64_t> permutation(
+  const U* keys, uint64_t n, int kind, int begin_bit, int end_bit, bool descending, bool single_tile_rule)
 {
-  std::vector<U> sk = striped_keys(keys, n, kind, begin_bit, end_bit, descending);
+  std::vector<U> sk = striped_keys(keys, n, kind, begin_bit, end_bit, descending, single_tile_rule);
   std::vector<uint64_t> perm(n);
   std::iota(perm.begin(), perm.end(), uint64_t(0));
   const U* p = sk.data();
@@ -124,7 +146,8 @@ int sort_impl(const void* keys_in,
 {
   const U* kin = static_cast<const U*>(keys_in);
   U* kout      = static_cast<U*>(keys_out);
-  std::vector<uint64_t> perm = permutation<U>(kin, n, kind, begin_bit, end_bit, descending != 0);
+  const bool single_tile_rule = n <= reference_single_tile_items(int(sizeof(U)), value_bytes);
+  std::vector<uint64_t> perm  = permutation<U>(kin, n, kind, begin_bit, end_bit, descending != 0, single_tile_rule);
   // catch2_radix_sort_helper.cuh:281-284, :305-309 (gather)
   for (uint64_t i = 0; i < n; ++i)
   {

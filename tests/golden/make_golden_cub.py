@@ -30,6 +30,17 @@ CASES = [
     ("cub_i16_bits0_9", np.int16, "uniform", 3000, np.uint32, False, (0, 9), False),
     ("cub_u8_desc", np.uint8, "uniform", 1000, np.uint32, True, None, False),
     ("cub_u32_keys_only", np.uint32, "uniform", 4096, None, False, None, False),
+    # above the reference's single-tile size (4864 / 2304 items): the onesweep kernels, whose float-zero rule for
+    # descending partial-window sorts differs from the single-tile kernel's (oracle/radix_sort_oracle.cpp)
+    ("cub_onesweep_f32_desc_bits8_24_zeros", np.float32, "uniform", 6000, np.uint32, True, (8, 24), True),
+    ("cub_onesweep_f32_asc_bits8_24_zeros", np.float32, "uniform", 6000, np.uint32, False, (8, 24), True),
+    ("cub_onesweep_f32_desc_bits0_9_zeros_keys", np.float32, "uniform", 5000, None, True, (0, 9), True),
+    ("cub_onesweep_f64_desc_bits5_63_zeros", np.float64, "uniform", 3000, np.uint32, True, (5, 63), True),
+    ("cub_onesweep_f64_desc_bits40_64_zeros_v64", np.float64, "uniform", 2400, np.uint64, True, (40, 64), True),
+    ("cub_single_f64_desc_bits40_64_zeros_v64", np.float64, "uniform", 2304, np.uint64, True, (40, 64), True),
+    ("cub_single_f32_desc_bits8_24_zeros_4864", np.float32, "uniform", 4864, np.uint32, True, (8, 24), True),
+    ("cub_onesweep_f32_desc_bits8_24_zeros_4865", np.float32, "uniform", 4865, np.uint32, True, (8, 24), True),
+    ("cub_onesweep_i32_desc_bits5_20", np.int32, "entropy3", 7001, np.uint32, True, (5, 20), False),
 ]
 
 

@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench line, ncu launch list, one full ncu capture of the top kernel.
+# usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag> [skip-tests]
+TAG=${1:-r1}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+if [ "$2" != "skip-tests" ]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+  tail -5 $OUT/pytest_gpu.log
+fi
+timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:onesweep_kernel -s 4 -c 1 -f -o $OUT/onesweep_full \
+  python tools/prof_one.py "sortkeys_u32_2^28_uniform" 0 2 > $OUT/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:histogram_kernel -s 1 -c 1 -f -o $OUT/histogram_full \
+  python tools/prof_one.py "sortkeys_u32_2^28_uniform" 0 2 >> $OUT/ncu_full.log 2>&1
+ls -la $OUT
