@@ -16,6 +16,7 @@ KEY_UINT, KEY_INT, KEY_FLOAT = 0, 1, 2
 EXPORTS = (
     "b200rs_version",
     "b200rs_sort",
+    "b200rs_sort_inplace",
     "b200rs_digit_histogram",
     "b200rs_splitter_ranks",
     "b200rs_last_launch_count",
@@ -52,6 +53,8 @@ def lib() -> ctypes.CDLL:
         l.b200rs_sort.restype = i32
         l.b200rs_sort.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, vp, vp, u64,
                                   i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(i32), vp]
+        l.b200rs_sort_inplace.restype = i32
+        l.b200rs_sort_inplace.argtypes = [vp, vp, u64, i32, i32, i32, i32, i32, vp]
         l.b200rs_digit_histogram.restype = i32
         l.b200rs_digit_histogram.argtypes = [vp, u64, i32, i32, i32, i32, i32, vp, vp]
         l.b200rs_splitter_ranks.restype = i32

@@ -221,6 +221,8 @@ struct PassArgs
   const unsigned long long* bins; // [256] exclusive global offsets of this pass (+ portion)
   unsigned long long* bins_next;  // next portion's offsets, written by the last tile (or nullptr)
   uint32_t num_items;      // items in this portion, < 2^30
+  uint32_t num_tiles;      // ceil(num_items / tile items of the launched configuration)
+  uint32_t all_ones;       // 0xffffffff, passed at run time so that x * all_ones + all_ones stays an IMAD (== ~x)
   int shift;               // first bit of the digit
   uint32_t mask;           // (1 << digit_bits) - 1
   int first_pass;          // transform on load

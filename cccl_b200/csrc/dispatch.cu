@@ -199,8 +199,8 @@ int b200rs_describe_config(int key_bytes, int value_bytes, int config_index, cha
   if (buf != nullptr && buf_len > 0)
   {
     const OnesweepConfig& c = tab[config_index];
-    snprintf(buf, buf_len, "k%dv%d threads=%d items=%d minb=%d tile=%d smem=%zu rank=%s", key_bytes, value_bytes, c.threads,
-             c.items_per_thread, c.min_blocks, c.tile_items, c.smem_bytes, c.rank_algo == 0 ? "match" : "ballot");
+    snprintf(buf, buf_len, "k%dv%d threads=%d items=%d minb=%d tile=%d smem=%zu", key_bytes, value_bytes, c.threads,
+             c.items_per_thread, c.min_blocks, c.tile_items, c.smem_bytes);
   }
   return count;
 }
@@ -492,6 +492,8 @@ int b200rs_sort(
       a.bins         = bins + (portion * passes + pass) * RADIX;
       a.bins_next    = (portion + 1 < portions) ? bins + ((portion + 1) * passes + pass) * RADIX : nullptr;
       a.num_items    = uint32_t(count);
+      a.num_tiles    = tiles;
+      a.all_ones     = 0xffffffffu;
       a.shift        = bit;
       a.mask         = (1u << nbits) - 1u;
       a.first_pass   = pass == 0;

@@ -3,9 +3,20 @@
 //
 // Replaces DeviceRadixSortHistogramKernel / AgentRadixSortHistogram and DeviceRadixSortExclusiveSumKernel
 // (/root/reference/cub/cub/device/dispatch/kernels/kernel_radix_sort.cuh:447-473, :563-606,
-//  cub/cub/agent/agent_radix_sort_histogram.cuh:118-121, :184-279).  Differences: 128-bit loads with the key
-// transform fused, a persistent grid sized from the SM count, COPIES lane-interleaved sub-histograms per pass so
-// that low-entropy inputs (all lanes hitting one bin) serialise COPIES times less, 64-bit global bins.
+//  cub/cub/agent/agent_radix_sort_histogram.cuh:118-121, :184-279).
+//
+// What bounds this kernel on B200 is the shared-memory atomic pipe, not HBM: ncu on the first version (4
+// interleaved sub-histograms, profiles/r1_histogram_*) showed the LSU wavefront pipe at 92 % with 13 wavefronts per
+// 32 keys -- 4 atomics per key, each ~3.3-way bank-conflicted because random digits of 32 lanes collide in the 32
+// banks -- and 43 instructions per key.  So:
+//   * REPLICAS sub-histograms per pass laid out bin-major, replica-minor: counter (pass, bin, replica) lives at word
+//     (pass*256 + bin)*REPLICAS + replica.  With REPLICAS == 32 and replica == lane, lane l only ever touches bank l:
+//     every warp-wide atomic is ONE conflict-free wavefront whatever the digits are (all-equal keys included).
+//     4-byte keys: 4 passes x 256 x 32 x 4 B = 128 KB; 8-byte keys use 16 replicas (2-way conflicts) to fit 8 passes;
+//   * one persistent CTA of 1024 threads per SM owns that shared memory;
+//   * no-return shared atomics (red.shared.add) on 32-bit shared-window addresses, 128-bit key loads, the key
+//     transform fused, the pass count a template parameter (no per-key branches);
+//   * 64-bit global bins, one global atomic per non-zero (pass, bin) per CTA.
 #pragma once
 
 #include "common.cuh"
@@ -13,45 +24,64 @@
 namespace b200rs
 {
 
-constexpr int HIST_THREADS = 512;
-constexpr int HIST_COPIES  = 4;
-constexpr int HIST_UNROLL  = 4; // 16-byte loads in flight per thread
+constexpr int HIST_THREADS = 1024;
+constexpr int HIST_UNROLL  = 2; // 16-byte loads in flight per thread
 
-template <class U, int MAXP>
-__device__ __forceinline__ void hist_accumulate(
-  U bits, const XformT<U>& xf, uint32_t* h_lane, int passes, int begin_bit, int end_bit)
+template <int KEY_BYTES>
+struct HistLayout
+{
+  static constexpr int MAXP     = KEY_BYTES;                    // at most one pass per key byte
+  static constexpr int REPLICAS = KEY_BYTES <= 4 ? 32 : 16;     // sub-histograms per pass
+  static constexpr size_t BYTES = size_t(MAXP) * RADIX * REPLICAS * 4;
+};
+
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
+{
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// `mine` = shared-window address of this thread's replica of (pass 0, bin 0)
+template <class U, int PASSES, int REPLICAS>
+__device__ __forceinline__ void hist_accumulate(U bits, const XformT<U>& xf, uint32_t mine, int begin_bit, int end_bit)
 {
   const U view = digit_view(twiddle_in(bits, xf), xf);
 #pragma unroll
-  for (int p = 0; p < MAXP; ++p)
+  for (int p = 0; p < PASSES; ++p)
   {
-    if (p < passes)
+    const int bit    = begin_bit + p * RADIX_BITS;
+    uint32_t d       = uint32_t(view >> bit);
+    if (p == PASSES - 1)
     {
-      const int bit       = begin_bit + p * RADIX_BITS;
-      const int nbits     = min(RADIX_BITS, end_bit - bit);
-      const uint32_t d    = uint32_t(view >> bit) & ((1u << nbits) - 1u);
-      atomicAdd(h_lane + p * (RADIX * HIST_COPIES) + d * HIST_COPIES, 1u);
+      d &= (1u << min(RADIX_BITS, end_bit - bit)) - 1u; // the last pass may be narrower than 8 bits
     }
+    else
+    {
+      d &= uint32_t(RADIX - 1);
+    }
+    red_shared_add(mine + (p * RADIX + d) * (REPLICAS * 4), 1u);
   }
 }
 
-// bins: [passes][256] uint64, zero on entry; accumulated with global atomics.
-template <class U>
-__global__ void __launch_bounds__(HIST_THREADS)
-histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long long* bins, int passes, int begin_bit,
-                 int end_bit, const KeyXform kx)
+// bins: [PASSES][256] uint64, zero on entry; accumulated with global atomics.
+template <class U, int PASSES>
+__global__ void __launch_bounds__(HIST_THREADS, 1)
+histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long long* bins, int begin_bit, int end_bit,
+                 const KeyXform kx)
 {
-  constexpr int MAXP = int(sizeof(U));          // at most one pass per key byte
-  constexpr int VEC  = 16 / int(sizeof(U));     // keys per 128-bit load
-  __shared__ uint32_t h[MAXP * RADIX * HIST_COPIES];
+  using L                = HistLayout<int(sizeof(U))>;
+  constexpr int REPLICAS = L::REPLICAS;
+  constexpr int VEC      = 16 / int(sizeof(U)); // keys per 128-bit load
+  extern __shared__ __align__(16) unsigned char hsmem[];
+  uint32_t* h          = reinterpret_cast<uint32_t*>(hsmem);
+  const uint32_t sbase = uint32_t(__cvta_generic_to_shared(hsmem));
 
   const XformT<U> xf(kx);
-  for (int i = threadIdx.x; i < MAXP * RADIX * HIST_COPIES; i += HIST_THREADS)
+  for (int i = threadIdx.x; i < PASSES * RADIX * REPLICAS; i += HIST_THREADS)
   {
     h[i] = 0;
   }
   __syncthreads();
-  uint32_t* h_lane = h + (threadIdx.x & (HIST_COPIES - 1));
+  const uint32_t mine = sbase + (threadIdx.x & (REPLICAS - 1)) * 4;
 
   // split [0,n) into a scalar head up to 16-byte alignment, a vector body and a scalar tail
   const unsigned long long addr = reinterpret_cast<unsigned long long>(keys);
@@ -67,15 +97,15 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
   {
     for (unsigned long long i = threadIdx.x; i < head; i += HIST_THREADS)
     {
-      hist_accumulate<U, MAXP>(keys[i], xf, h_lane, passes, begin_bit, end_bit);
+      hist_accumulate<U, PASSES, REPLICAS>(keys[i], xf, mine, begin_bit, end_bit);
     }
     for (unsigned long long i = tail + threadIdx.x; i < n; i += HIST_THREADS)
     {
-      hist_accumulate<U, MAXP>(keys[i], xf, h_lane, passes, begin_bit, end_bit);
+      hist_accumulate<U, PASSES, REPLICAS>(keys[i], xf, mine, begin_bit, end_bit);
     }
   }
 
-  const uint4* vkeys = reinterpret_cast<const uint4*>(keys + head);
+  const uint4* vkeys              = reinterpret_cast<const uint4*>(keys + head);
   const unsigned long long stride = (unsigned long long) gridDim.x * HIST_THREADS;
   unsigned long long v            = (unsigned long long) blockIdx.x * HIST_THREADS + threadIdx.x;
   // main loop: HIST_UNROLL independent 16-byte loads per thread, each warp instruction covers 512 contiguous bytes
@@ -94,7 +124,7 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
 #pragma unroll
       for (int j = 0; j < VEC; ++j)
       {
-        hist_accumulate<U, MAXP>(e[j], xf, h_lane, passes, begin_bit, end_bit);
+        hist_accumulate<U, PASSES, REPLICAS>(e[j], xf, mine, begin_bit, end_bit);
       }
     }
   }
@@ -105,22 +135,23 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
 #pragma unroll
     for (int j = 0; j < VEC; ++j)
     {
-      hist_accumulate<U, MAXP>(e[j], xf, h_lane, passes, begin_bit, end_bit);
+      hist_accumulate<U, PASSES, REPLICAS>(e[j], xf, mine, begin_bit, end_bit);
     }
   }
   __syncthreads();
 
-  for (int i = threadIdx.x; i < passes * RADIX; i += HIST_THREADS)
+  // fold the replicas: consecutive threads read consecutive words (conflict-free), REPLICAS-wide segmented sum by shuffles
+  for (int i = threadIdx.x; i < PASSES * RADIX * REPLICAS; i += HIST_THREADS)
   {
-    unsigned long long c = 0;
+    unsigned long long c = h[i];
 #pragma unroll
-    for (int k = 0; k < HIST_COPIES; ++k)
+    for (int s = REPLICAS / 2; s > 0; s >>= 1)
     {
-      c += h[i * HIST_COPIES + k];
+      c += __shfl_down_sync(0xffffffffu, c, s, REPLICAS);
     }
-    if (c != 0)
+    if ((threadIdx.x & (REPLICAS - 1)) == 0 && c != 0)
     {
-      atomicAdd(bins + i, c);
+      atomicAdd(bins + i / REPLICAS, c);
     }
   }
 }

@@ -7,22 +7,22 @@ using K = uint16_t;
 #define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
 
 static const OnesweepConfig cfg_v0[] = {
-  C(0, 512, 16, 2)
+  C(0, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v1[] = {
-  C(1, 512, 16, 2)
+  C(1, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v2[] = {
-  C(2, 512, 16, 2)
+  C(2, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v4[] = {
-  C(4, 512, 16, 2)
+  C(4, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v8[] = {
-  C(8, 512, 12, 2)
+  C(8, 256, 20, 3)
 };
 static const OnesweepConfig cfg_v16[] = {
-  C(16, 512, 8, 2)
+  C(16, 256, 12, 3)
 };
 
 #define B200RS_TABLE(arr)                     \

@@ -7,39 +7,28 @@ using K = uint32_t;
 #define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
 
 static const OnesweepConfig cfg_v0[] = {
-  C(0, 512, 16, 2),
-  C(0, 384, 16, 3),
-  C(0, 384, 20, 2),
-  C(0, 256, 16, 4),
-  C(0, 256, 24, 3),
-  C(0, 512, 12, 2),
-  C(0, 512, 20, 2),
-  C(0, 1024, 8, 1),
-  C(0, 1024, 12, 1),
-  C(0, 1024, 16, 1),
-  C(0, 512, 16, 1),
+  C(0, 256, 32, 4),
+  C(0, 256, 40, 3),
+  C(0, 512, 24, 2),
   make_config<K, 0, 512, 16, RANK_MATCH, 2>() // MATCH.ANY, kept for measurement
 };
 static const OnesweepConfig cfg_v1[] = {
-  C(1, 512, 16, 2)
+  C(1, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v2[] = {
-  C(2, 512, 16, 2)
+  C(2, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v4[] = {
-  C(4, 512, 16, 2),
-  C(4, 512, 12, 2),
-  C(4, 384, 16, 2),
-  C(4, 384, 16, 3),
-  C(4, 256, 16, 3),
-  C(4, 256, 16, 4),
-  C(4, 1024, 8, 1),
-  C(4, 1024, 12, 1)
+  C(4, 256, 36, 3),
+  C(4, 256, 32, 3),
+  C(4, 512, 20, 2)
 };
 static const OnesweepConfig cfg_v8[] = {
+  C(8, 256, 20, 3),
   C(8, 512, 12, 2)
 };
 static const OnesweepConfig cfg_v16[] = {
+  C(16, 256, 12, 3),
   C(16, 512, 8, 2)
 };
 

@@ -7,35 +7,27 @@ using K = uint64_t;
 #define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
 
 static const OnesweepConfig cfg_v0[] = {
-  C(0, 512, 8, 2),
-  C(0, 512, 12, 2),
-  C(0, 512, 12, 1),
-  C(0, 384, 12, 2),
-  C(0, 384, 12, 3),
-  C(0, 256, 16, 2),
-  C(0, 256, 12, 4),
-  C(0, 1024, 8, 1)
+  C(0, 256, 24, 3),
+  C(0, 256, 32, 2),
+  C(0, 512, 16, 2)
 };
 static const OnesweepConfig cfg_v1[] = {
-  C(1, 512, 12, 2)
+  C(1, 256, 24, 3)
 };
 static const OnesweepConfig cfg_v2[] = {
-  C(2, 512, 12, 2)
+  C(2, 256, 24, 3)
 };
 static const OnesweepConfig cfg_v4[] = {
-  C(4, 512, 8, 2),
-  C(4, 512, 12, 2),
-  C(4, 512, 12, 1),
-  C(4, 384, 12, 2),
-  C(4, 384, 12, 3),
-  C(4, 256, 16, 2),
-  C(4, 256, 12, 4),
-  C(4, 1024, 8, 1)
+  C(4, 256, 24, 3),
+  C(4, 256, 20, 3),
+  C(4, 512, 14, 2)
 };
 static const OnesweepConfig cfg_v8[] = {
+  C(8, 256, 16, 3),
   C(8, 512, 12, 2)
 };
 static const OnesweepConfig cfg_v16[] = {
+  C(16, 256, 10, 3),
   C(16, 512, 8, 2)
 };
 

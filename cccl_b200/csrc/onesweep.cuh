@@ -12,9 +12,9 @@
 //   * no "early counts" histogram pre-pass over the tile: the warp-private running offsets that ranking
 //     maintains ARE the per-warp digit histograms once the last item is ranked (saves one shared atomic
 //     per key);
-//   * match-by-ballot written so each digit bit costs ~3 SASS instructions (VOTE, predicated NOT, AND; the
-//     eight predicates come from one R2P + one LOP3.P); MATCH.ANY is kept as a template switch for measurement
-//     only -- it runs at ~1 per 40 cycles per SM on B200 and loses by 1.6x;
+//   * match-by-ballot: the eight digit-bit predicates come from two R2P (four bits each), then per bit one VOTE and
+//     one predicated NOT, and the eight complemented ballots are ANDed three at a time (3 LOP3); MATCH.ANY is kept
+//     as a template switch for measurement only -- it runs at ~1 per 40 cycles per SM on B200 and loses by 1.6x;
 //   * the highest peer lane is the leader, so ONE POPC per key gives both the lane's rank among its peers
 //     and (for the leader) the group size;
 //   * shared memory is addressed with explicit 32-bit shared-window addresses (one LEA per access);
@@ -145,25 +145,47 @@ __device__ __forceinline__ void sts_t(uint32_t addr, T v)
 
 // lanes of the warp whose 8-bit digit equals this lane's: per bit {predicate, ballot, flip for lanes whose bit is
 // clear, and}.  Bits above the pass's digit width are zero in every lane and cost nothing in correctness.
-__device__ __forceinline__ uint32_t match_digit_ballot(uint32_t d)
+__device__ __forceinline__ void match_digit_ballot(uint32_t d, uint32_t& b, uint32_t& c)
 {
-  uint32_t peers;
+  // Returned as two words whose AND is the peer mask: the caller folds that AND into its own three-input LOP3s.
+  // The digit bits are tested four at a time so that ptxas packs each group into ONE R2P (register bits ->
+  // predicates) and never needs more than four predicates at once; the complemented ballots are combined with
+  // three-input ANDs (3 LOP3 instead of 7).
   asm volatile(
     "{\n"
-    ".reg .pred p;\n"
-    ".reg .b32 v, t;\n"
-    "and.b32 t, %1, 1;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 %0, p, 0xffffffff; @!p not.b32 %0, %0;\n"
-    "and.b32 t, %1, 2;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-    "and.b32 t, %1, 4;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-    "and.b32 t, %1, 8;   setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-    "and.b32 t, %1, 16;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-    "and.b32 t, %1, 32;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-    "and.b32 t, %1, 64;  setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
-    "and.b32 t, %1, 128; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 v, p, 0xffffffff; @!p not.b32 v, v; and.b32 %0, %0, v;\n"
+    ".reg .pred p0, p1, p2, p3;\n"
+    ".reg .b32 v0, v1, v2, v3, v4, v5, v6, v7, t, dh;\n"
+    "shr.u32 dh, %2, 4;\n"
+    "and.b32 t, %2, 1; setp.ne.u32 p0, t, 0;\n"
+    "and.b32 t, %2, 2; setp.ne.u32 p1, t, 0;\n"
+    "and.b32 t, %2, 4; setp.ne.u32 p2, t, 0;\n"
+    "and.b32 t, %2, 8; setp.ne.u32 p3, t, 0;\n"
+    "vote.sync.ballot.b32 v0, p0, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v1, p1, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v2, p2, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v3, p3, 0xffffffff;\n"
+    "@!p0 not.b32 v0, v0;\n"
+    "@!p1 not.b32 v1, v1;\n"
+    "@!p2 not.b32 v2, v2;\n"
+    "@!p3 not.b32 v3, v3;\n"
+    "and.b32 t, dh, 1; setp.ne.u32 p0, t, 0;\n"
+    "and.b32 t, dh, 2; setp.ne.u32 p1, t, 0;\n"
+    "and.b32 t, dh, 4; setp.ne.u32 p2, t, 0;\n"
+    "and.b32 t, dh, 8; setp.ne.u32 p3, t, 0;\n"
+    "vote.sync.ballot.b32 v4, p0, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v5, p1, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v6, p2, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v7, p3, 0xffffffff;\n"
+    "@!p0 not.b32 v4, v4;\n"
+    "@!p1 not.b32 v5, v5;\n"
+    "@!p2 not.b32 v6, v6;\n"
+    "@!p3 not.b32 v7, v7;\n"
+    "lop3.b32 t, v0, v1, v2, 0x80;\n"
+    "lop3.b32 %0, v3, v4, v5, 0x80;\n"
+    "lop3.b32 %1, v6, v7, t, 0x80;\n"
     "}\n"
-    : "=&r"(peers)
+    : "=r"(b), "=r"(c)
     : "r"(d));
-  return peers;
 }
 
 template <int N>
@@ -256,11 +278,19 @@ __device__ __forceinline__ void onesweep_tile(
   for (int i = 0; i < IPT; ++i)
   {
     const uint32_t d      = pass_digit<FLOATK>(key[i], shift, dmask, neg_zero, pos_zero);
-    const uint32_t peers  = (RANK == RANK_MATCH) ? __match_any_sync(0xffffffffu, d) : match_digit_ballot(d);
-    const uint32_t before = __popc(peers & lt_mask);
+    uint32_t b, c; // peers == b & c
+    if (RANK == RANK_MATCH)
+    {
+      b = c = __match_any_sync(0xffffffffu, d);
+    }
+    else
+    {
+      match_digit_ballot(d, b, c);
+    }
+    const uint32_t before = __popc(b & c & lt_mask);
     const uint32_t ctr    = s_mine + d * 4;
     const uint32_t off    = lds32(ctr);
-    if ((peers & gt_mask) == 0) // highest peer lane: its `before` + 1 is the group size
+    if ((b & c & gt_mask) == 0) // highest peer lane: its `before` + 1 is the group size
     {
       sts32(ctr, off + before + 1);
     }

@@ -5,22 +5,52 @@
 namespace b200rs
 {
 
+template <class U, int PASSES>
+static cudaError_t launch_hist_p(
+  const void* keys, unsigned long long n, unsigned long long* bins, int begin_bit, int end_bit, const KeyXform& xf,
+  unsigned grid, cudaStream_t stream)
+{
+  using L     = HistLayout<int(sizeof(U))>;
+  auto kernel = histogram_kernel<U, PASSES>;
+  const size_t smem = size_t(PASSES) * RADIX * L::REPLICAS * 4;
+  if (smem > 48 * 1024)
+  {
+    // per-device attribute; cheap and idempotent, legal during stream capture
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess)
+    {
+      return e;
+    }
+  }
+  kernel<<<grid, HIST_THREADS, smem, stream>>>(static_cast<const U*>(keys), n, bins, begin_bit, end_bit, xf);
+  return cudaPeekAtLastError();
+}
+
 template <class U>
 static cudaError_t launch_hist_t(
   const void* keys, unsigned long long n, unsigned long long* bins, int passes, int begin_bit, int end_bit,
   const KeyXform& xf, int sm_count, cudaStream_t stream)
 {
   constexpr unsigned long long VEC = 16 / sizeof(U);
-  // persistent grid: a multiple of the SM count (4 x 512 threads fill an SM), never more blocks than work
+  // persistent grid: one 1024-thread CTA per SM (it owns up to 128 KB of replicated counters), never more CTAs than work
   unsigned long long want = (n / VEC + HIST_THREADS * HIST_UNROLL - 1) / (HIST_THREADS * HIST_UNROLL);
-  unsigned grid           = unsigned(sm_count) * 4u;
+  unsigned grid           = unsigned(sm_count);
   if (want < grid)
   {
     grid = want < 1 ? 1u : unsigned(want);
   }
-  histogram_kernel<U><<<grid, HIST_THREADS, 0, stream>>>(static_cast<const U*>(keys), n, bins, passes, begin_bit,
-                                                           end_bit, xf);
-  return cudaPeekAtLastError();
+  switch (passes)
+  {
+    case 1: return launch_hist_p<U, 1>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    case 2: return launch_hist_p<U, (sizeof(U) >= 2 ? 2 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    case 3: return launch_hist_p<U, (sizeof(U) >= 4 ? 3 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    case 4: return launch_hist_p<U, (sizeof(U) >= 4 ? 4 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    case 5: return launch_hist_p<U, (sizeof(U) >= 8 ? 5 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    case 6: return launch_hist_p<U, (sizeof(U) >= 8 ? 6 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    case 7: return launch_hist_p<U, (sizeof(U) >= 8 ? 7 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    case 8: return launch_hist_p<U, (sizeof(U) >= 8 ? 8 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launch_histogram(

@@ -102,6 +102,27 @@ B200RS_API int b200rs_sort(
   b200rs_stream_t stream);
 
 /*
+ * In-place sort of device memory: the thrust::sort / thrust::sort_by_key front door (full key width).
+ *
+ * Replaces thrust::cuda_cub::__radix_sort::radix_sort + the tail of __smart_sort::smart_sort
+ * (/root/reference/thrust/thrust/system/cuda/detail/sort.h:219-266, :288-339): obtains scratch for the alternate
+ * buffers and the temp blob (stream-ordered pool of the current device instead of the reference's cudaMalloc /
+ * cudaFree per call), runs the DoubleBuffer sort, copies back iff the result landed in the scratch half, releases the
+ * scratch; `synchronize` != 0 additionally waits for the stream (the reference's synchronize_optional).
+ * d_values is ignored when value_bytes == 0.  thrust::less => descending = 0, thrust::greater => descending = 1.
+ */
+B200RS_API int b200rs_sort_inplace(
+  void* d_keys,
+  void* d_values,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int descending,
+  int synchronize,
+  b200rs_stream_t stream);
+
+/*
  * The upsweep on its own: one read of the keys produces the digit histogram of every 8-bit pass.
  * d_bins is a device array of uint64[ceil((end_bit-begin_bit)/8) * 256], overwritten.
  *
