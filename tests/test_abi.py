@@ -39,7 +39,7 @@ def test_size_query_is_pure_and_deterministic():
     c, _ = _query(1 << 20, 4, 0, 0, 32, True)
     assert a - c >= (1 << 20) * 4  # pointer API carries an extra key buffer (device_radix_sort.cuh:310-315)
     d, _ = _query(1 << 20, 4, 4, 0, 32, False)
-    assert d - a >= (1 << 20) * 4 - 4096
+    assert d - a >= (1 << 20) * 4 - (64 << 10)  # the tile (hence look-back array) size differs per type pair
     one_pass, _ = _query(1 << 20, 4, 0, 0, 8, False)
     assert one_pass < (1 << 20)  # single pass goes straight from in to out
 
