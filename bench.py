@@ -383,6 +383,14 @@ def run_single_gpu(args):
 
 
 def run_multi_gpu(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        # launched as plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        import subprocess
+
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)]
+        raise SystemExit(subprocess.call(cmd + sys.argv[1:]))
     from cccl_b200 import multi_gpu_bench
 
     multi_gpu_bench.run(args, METRIC, DEFAULT_NGPU, ClockSampler, measured_peaks)
