@@ -163,6 +163,26 @@ def cpu_reference_run(steps, warmup, log2n=24, threads=None):
     }
 
 
+def cub_same_gpu(kdt, vb, log2n, dist, desc, b, e, iters=10):
+    """Context number: the UNMODIFIED reference cub::DeviceRadixSort (oracle/_ref/ref_cub_radix_sort, built from the
+    reference headers for sm_100a) on the same GPU and input shape.  Separate process; reported, never on our path."""
+    import subprocess
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_cub_radix_sort")
+    kt = {"uint32": "u32", "uint64": "u64", "float32": "f32", "int64": "i64"}[kdt]
+    if not os.path.exists(exe) or vb not in (0, 4, 8):
+        return None
+    rounds = int(dist[7:]) if dist.startswith("entropy") else 1
+    try:
+        out = subprocess.run([exe, "bench", kt, str(vb), str(log2n), str(int(desc)), str(b), str(e), str(rounds),
+                              str(iters)], capture_output=True, text=True, timeout=300).stdout
+        r = json.loads(out.strip().splitlines()[-1])
+        return {"value": r["gkeys_s"], "unit": "Gkeys/s", "ms_per_step": r["ms"], "impl": r["impl"],
+                "temp_bytes": r["temp_bytes"]}
+    except Exception as ex:  # context only
+        return {"unavailable": str(ex)[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -354,6 +374,8 @@ def run_single_gpu(args):
         r = cpu_reference_run(3, 1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    cub = None if args.no_cub else cub_same_gpu(kdt, vb, log2n, dist, desc, b, e)
+
     line = {
         "metric": METRIC,
         "value": value,
@@ -373,6 +395,7 @@ def run_single_gpu(args):
                    "tile_config": _native.describe_configs(kb, vb)[args.config or 0]},
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "cub_same_gpu": cub,
         "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
@@ -405,6 +428,7 @@ def main():
     ap.add_argument("--workload", default=None, help="one of: " + ", ".join(WORKLOADS))
     ap.add_argument("--config", type=int, default=None, help="force an onesweep tile configuration index")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cub", action="store_true", help="skip the cub-on-the-same-GPU context run")
     ap.add_argument("--log2-per-gpu", type=int, default=28, help="multi-GPU: log2 of pairs per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -1,0 +1,455 @@
+// cub::DeviceRadixSort on top of libb200rs.so -- a header-only drop-in for the arithmetic-key surface of
+// /root/reference/cub/cub/device/device_radix_sort.cuh (cub 3.6.0).
+//
+// Put this repo's include/ ahead of the CCCL include path and link -lb200rs.  Every overload below keeps the
+// reference's name, template parameters that matter for deduction, parameter order and defaults, and returns
+// cudaError_t; each one type-erases to ONE call of the C ABI (include/b200rs.h, b200rs_sort).  Nothing here
+// contains a kernel and nothing falls back to another implementation: an unsupported key type is a compile error,
+// an unsupported size a cudaErrorNotSupported from the library.
+//
+//   reference overload (device_radix_sort.cuh)            here
+//   SortPairs            pointer :412   DoubleBuffer :1127   env :532 / :1230
+//   SortPairsDescending  pointer :1776  DoubleBuffer :2295   env :1894 / :2398
+//   SortKeys             pointer :3034  DoubleBuffer :3644   env :3138 / :3743
+//   SortKeysDescending   pointer :4211  DoubleBuffer :4669   env :4310 / :4768
+// Not provided ("next"): the decomposer overloads for user-defined key types.
+//
+// Semantics kept from the reference:
+//   * d_temp_storage == nullptr  => only temp_storage_bytes is written (device_radix_sort.cuh:300-317);
+//   * pointer overloads never write the input and need ~N extra temp; DoubleBuffer overloads may clobber both
+//     buffers, need O(N / tile) temp, and flip d_keys.selector / d_values.selector to the buffer holding the
+//     result (dispatch_radix_sort.cuh:1943-1944);
+//   * keys are ordered by bits [begin_bit, end_bit) of Traits<KeyT>::TwiddleIn(key) (util_type.cuh:857-963),
+//     -0.0 == +0.0, stable in both directions;
+//   * work is enqueued on `stream` without synchronisation; legal under stream capture.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <type_traits>
+
+#include "../../b200rs.h"
+
+namespace cub
+{
+
+/// Same layout and members as cub::DoubleBuffer (/root/reference/cub/cub/util_type.cuh:749-779).
+template <typename T>
+struct DoubleBuffer
+{
+  T* d_buffers[2]{};
+  int selector = 0;
+
+  DoubleBuffer() = default;
+  __host__ __device__ DoubleBuffer(T* d_current, T* d_alternate)
+      : d_buffers{d_current, d_alternate}
+  {}
+  __host__ __device__ T* Current()
+  {
+    return d_buffers[selector];
+  }
+  __host__ __device__ T* Alternate()
+  {
+    return d_buffers[selector ^ 1];
+  }
+};
+
+/// Placeholder value type of keys-only sorts (/root/reference/cub/cub/util_type.cuh NullType).
+struct NullType
+{};
+
+enum class SortOrder
+{
+  Ascending,
+  Descending
+};
+
+namespace detail
+{
+// Traits<T>::CATEGORY of the reference (util_type.cuh:857-963) reduced to what the transform needs.
+template <class KeyT>
+constexpr int b200rs_key_kind_of()
+{
+  using K = std::remove_cv_t<KeyT>;
+  static_assert(std::is_arithmetic<K>::value,
+                "this drop-in covers arithmetic keys; decomposer / user-defined keys are not built (SURVEY 8f)");
+  static_assert(sizeof(K) == 1 || sizeof(K) == 2 || sizeof(K) == 4 || sizeof(K) == 8, "key width must be 1/2/4/8");
+  return std::is_floating_point<K>::value ? B200RS_KEY_FLOAT
+       : (std::is_signed<K>::value && !std::is_same<K, bool>::value) ? B200RS_KEY_INT
+                                                                     : B200RS_KEY_UINT;
+}
+template <class ValueT>
+constexpr int b200rs_value_bytes_of()
+{
+  return std::is_same<std::remove_cv_t<ValueT>, NullType>::value ? 0 : int(sizeof(ValueT));
+}
+
+template <class KeyT, class ValueT>
+inline cudaError_t b200rs_pointer_sort(
+  void* d_temp_storage,
+  size_t& temp_storage_bytes,
+  const KeyT* d_keys_in,
+  KeyT* d_keys_out,
+  const ValueT* d_values_in,
+  ValueT* d_values_out,
+  unsigned long long num_items,
+  int begin_bit,
+  int end_bit,
+  bool descending,
+  cudaStream_t stream)
+{
+  return static_cast<cudaError_t>(b200rs_sort(
+    d_temp_storage,
+    &temp_storage_bytes,
+    d_keys_in,
+    d_keys_out,
+    d_values_in,
+    d_values_out,
+    num_items,
+    b200rs_key_kind_of<KeyT>(),
+    int(sizeof(KeyT)),
+    b200rs_value_bytes_of<ValueT>(),
+    begin_bit,
+    end_bit,
+    descending ? 1 : 0,
+    /*is_overwrite_okay=*/0,
+    nullptr,
+    reinterpret_cast<b200rs_stream_t>(stream)));
+}
+
+template <class KeyT, class ValueT>
+inline cudaError_t b200rs_double_buffer_sort(
+  void* d_temp_storage,
+  size_t& temp_storage_bytes,
+  DoubleBuffer<KeyT>& d_keys,
+  DoubleBuffer<ValueT>* d_values,
+  unsigned long long num_items,
+  int begin_bit,
+  int end_bit,
+  bool descending,
+  cudaStream_t stream)
+{
+  int selector = 0;
+  const int rc = b200rs_sort(
+    d_temp_storage,
+    &temp_storage_bytes,
+    d_keys.Current(),
+    d_keys.Alternate(),
+    d_values ? static_cast<const void*>(d_values->Current()) : nullptr,
+    d_values ? static_cast<void*>(d_values->Alternate()) : nullptr,
+    num_items,
+    b200rs_key_kind_of<KeyT>(),
+    int(sizeof(KeyT)),
+    d_values ? b200rs_value_bytes_of<ValueT>() : 0,
+    begin_bit,
+    end_bit,
+    descending ? 1 : 0,
+    /*is_overwrite_okay=*/1,
+    &selector,
+    reinterpret_cast<b200rs_stream_t>(stream));
+  if (rc == 0 && d_temp_storage != nullptr)
+  {
+    d_keys.selector ^= selector; // dispatch_radix_sort.cuh:1943-1944
+    if (d_values)
+    {
+      d_values->selector ^= selector;
+    }
+  }
+  return static_cast<cudaError_t>(rc);
+}
+} // namespace detail
+
+/// Execution environment of the env overloads: the reference takes a cuda::std::execution::env carrying a stream
+/// and a memory resource (device_radix_sort.cuh:532, detail::dispatch_with_env); this stand-alone shim carries the
+/// stream and obtains the temporary storage from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync).
+struct stream_env
+{
+  cudaStream_t stream = nullptr;
+  stream_env()        = default;
+  stream_env(cudaStream_t s)
+      : stream(s)
+  {}
+};
+
+namespace detail
+{
+template <class F>
+inline cudaError_t b200rs_with_env(const stream_env& env, F&& call)
+{
+  size_t bytes    = 0;
+  cudaError_t err = call(nullptr, bytes, env.stream);
+  if (err != cudaSuccess)
+  {
+    return err;
+  }
+  void* d_temp = nullptr;
+  err          = cudaMallocAsync(&d_temp, bytes, env.stream);
+  if (err != cudaSuccess)
+  {
+    return err;
+  }
+  err                   = call(d_temp, bytes, env.stream);
+  const cudaError_t fre = cudaFreeAsync(d_temp, env.stream);
+  return err != cudaSuccess ? err : fre;
+}
+} // namespace detail
+
+struct DeviceRadixSort
+{
+  // ------------------------------------------------------------------ SortPairs
+  template <typename KeyT, typename ValueT, typename NumItemsT>
+  static cudaError_t SortPairs(
+    void* d_temp_storage,
+    size_t& temp_storage_bytes,
+    const KeyT* d_keys_in,
+    KeyT* d_keys_out,
+    const ValueT* d_values_in,
+    ValueT* d_values_out,
+    NumItemsT num_items,
+    int begin_bit       = 0,
+    int end_bit         = sizeof(KeyT) * 8,
+    cudaStream_t stream = nullptr)
+  {
+    return detail::b200rs_pointer_sort(
+      d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in, d_values_out,
+      static_cast<unsigned long long>(num_items), begin_bit, end_bit, false, stream);
+  }
+
+  template <typename KeyT, typename ValueT, typename NumItemsT>
+  static cudaError_t SortPairs(
+    void* d_temp_storage,
+    size_t& temp_storage_bytes,
+    DoubleBuffer<KeyT>& d_keys,
+    DoubleBuffer<ValueT>& d_values,
+    NumItemsT num_items,
+    int begin_bit       = 0,
+    int end_bit         = sizeof(KeyT) * 8,
+    cudaStream_t stream = nullptr)
+  {
+    return detail::b200rs_double_buffer_sort(
+      d_temp_storage, temp_storage_bytes, d_keys, &d_values, static_cast<unsigned long long>(num_items), begin_bit,
+      end_bit, false, stream);
+  }
+
+  template <typename KeyT, typename ValueT, typename NumItemsT,
+            std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  [[nodiscard]] static cudaError_t SortPairs(
+    const KeyT* d_keys_in,
+    KeyT* d_keys_out,
+    const ValueT* d_values_in,
+    ValueT* d_values_out,
+    NumItemsT num_items,
+    int begin_bit         = 0,
+    int end_bit           = sizeof(KeyT) * 8,
+    const stream_env& env = {})
+  {
+    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+      return SortPairs(t, b, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items, begin_bit, end_bit, s);
+    });
+  }
+
+  template <typename KeyT, typename ValueT, typename NumItemsT,
+            std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  [[nodiscard]] static cudaError_t SortPairs(
+    DoubleBuffer<KeyT>& d_keys,
+    DoubleBuffer<ValueT>& d_values,
+    NumItemsT num_items,
+    int begin_bit         = 0,
+    int end_bit           = sizeof(KeyT) * 8,
+    const stream_env& env = {})
+  {
+    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+      return SortPairs(t, b, d_keys, d_values, num_items, begin_bit, end_bit, s);
+    });
+  }
+
+  // ------------------------------------------------------------------ SortPairsDescending
+  template <typename KeyT, typename ValueT, typename NumItemsT>
+  static cudaError_t SortPairsDescending(
+    void* d_temp_storage,
+    size_t& temp_storage_bytes,
+    const KeyT* d_keys_in,
+    KeyT* d_keys_out,
+    const ValueT* d_values_in,
+    ValueT* d_values_out,
+    NumItemsT num_items,
+    int begin_bit       = 0,
+    int end_bit         = sizeof(KeyT) * 8,
+    cudaStream_t stream = nullptr)
+  {
+    return detail::b200rs_pointer_sort(
+      d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in, d_values_out,
+      static_cast<unsigned long long>(num_items), begin_bit, end_bit, true, stream);
+  }
+
+  template <typename KeyT, typename ValueT, typename NumItemsT>
+  static cudaError_t SortPairsDescending(
+    void* d_temp_storage,
+    size_t& temp_storage_bytes,
+    DoubleBuffer<KeyT>& d_keys,
+    DoubleBuffer<ValueT>& d_values,
+    NumItemsT num_items,
+    int begin_bit       = 0,
+    int end_bit         = sizeof(KeyT) * 8,
+    cudaStream_t stream = nullptr)
+  {
+    return detail::b200rs_double_buffer_sort(
+      d_temp_storage, temp_storage_bytes, d_keys, &d_values, static_cast<unsigned long long>(num_items), begin_bit,
+      end_bit, true, stream);
+  }
+
+  template <typename KeyT, typename ValueT, typename NumItemsT,
+            std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  [[nodiscard]] static cudaError_t SortPairsDescending(
+    const KeyT* d_keys_in,
+    KeyT* d_keys_out,
+    const ValueT* d_values_in,
+    ValueT* d_values_out,
+    NumItemsT num_items,
+    int begin_bit         = 0,
+    int end_bit           = sizeof(KeyT) * 8,
+    const stream_env& env = {})
+  {
+    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+      return SortPairsDescending(t, b, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items, begin_bit,
+                                 end_bit, s);
+    });
+  }
+
+  template <typename KeyT, typename ValueT, typename NumItemsT,
+            std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  [[nodiscard]] static cudaError_t SortPairsDescending(
+    DoubleBuffer<KeyT>& d_keys,
+    DoubleBuffer<ValueT>& d_values,
+    NumItemsT num_items,
+    int begin_bit         = 0,
+    int end_bit           = sizeof(KeyT) * 8,
+    const stream_env& env = {})
+  {
+    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+      return SortPairsDescending(t, b, d_keys, d_values, num_items, begin_bit, end_bit, s);
+    });
+  }
+
+  // ------------------------------------------------------------------ SortKeys
+  template <typename KeyT, typename NumItemsT>
+  static cudaError_t SortKeys(
+    void* d_temp_storage,
+    size_t& temp_storage_bytes,
+    const KeyT* d_keys_in,
+    KeyT* d_keys_out,
+    NumItemsT num_items,
+    int begin_bit       = 0,
+    int end_bit         = sizeof(KeyT) * 8,
+    cudaStream_t stream = nullptr)
+  {
+    return detail::b200rs_pointer_sort<KeyT, NullType>(
+      d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, nullptr, nullptr,
+      static_cast<unsigned long long>(num_items), begin_bit, end_bit, false, stream);
+  }
+
+  template <typename KeyT, typename NumItemsT>
+  static cudaError_t SortKeys(
+    void* d_temp_storage,
+    size_t& temp_storage_bytes,
+    DoubleBuffer<KeyT>& d_keys,
+    NumItemsT num_items,
+    int begin_bit       = 0,
+    int end_bit         = sizeof(KeyT) * 8,
+    cudaStream_t stream = nullptr)
+  {
+    return detail::b200rs_double_buffer_sort<KeyT, NullType>(
+      d_temp_storage, temp_storage_bytes, d_keys, nullptr, static_cast<unsigned long long>(num_items), begin_bit,
+      end_bit, false, stream);
+  }
+
+  template <typename KeyT, typename NumItemsT, std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  [[nodiscard]] static cudaError_t SortKeys(
+    const KeyT* d_keys_in,
+    KeyT* d_keys_out,
+    NumItemsT num_items,
+    int begin_bit         = 0,
+    int end_bit           = sizeof(KeyT) * 8,
+    const stream_env& env = {})
+  {
+    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+      return SortKeys(t, b, d_keys_in, d_keys_out, num_items, begin_bit, end_bit, s);
+    });
+  }
+
+  template <typename KeyT, typename NumItemsT, std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  [[nodiscard]] static cudaError_t SortKeys(
+    DoubleBuffer<KeyT>& d_keys,
+    NumItemsT num_items,
+    int begin_bit         = 0,
+    int end_bit           = sizeof(KeyT) * 8,
+    const stream_env& env = {})
+  {
+    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+      return SortKeys(t, b, d_keys, num_items, begin_bit, end_bit, s);
+    });
+  }
+
+  // ------------------------------------------------------------------ SortKeysDescending
+  template <typename KeyT, typename NumItemsT>
+  static cudaError_t SortKeysDescending(
+    void* d_temp_storage,
+    size_t& temp_storage_bytes,
+    const KeyT* d_keys_in,
+    KeyT* d_keys_out,
+    NumItemsT num_items,
+    int begin_bit       = 0,
+    int end_bit         = sizeof(KeyT) * 8,
+    cudaStream_t stream = nullptr)
+  {
+    return detail::b200rs_pointer_sort<KeyT, NullType>(
+      d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, nullptr, nullptr,
+      static_cast<unsigned long long>(num_items), begin_bit, end_bit, true, stream);
+  }
+
+  template <typename KeyT, typename NumItemsT>
+  static cudaError_t SortKeysDescending(
+    void* d_temp_storage,
+    size_t& temp_storage_bytes,
+    DoubleBuffer<KeyT>& d_keys,
+    NumItemsT num_items,
+    int begin_bit       = 0,
+    int end_bit         = sizeof(KeyT) * 8,
+    cudaStream_t stream = nullptr)
+  {
+    return detail::b200rs_double_buffer_sort<KeyT, NullType>(
+      d_temp_storage, temp_storage_bytes, d_keys, nullptr, static_cast<unsigned long long>(num_items), begin_bit,
+      end_bit, true, stream);
+  }
+
+  template <typename KeyT, typename NumItemsT, std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  [[nodiscard]] static cudaError_t SortKeysDescending(
+    const KeyT* d_keys_in,
+    KeyT* d_keys_out,
+    NumItemsT num_items,
+    int begin_bit         = 0,
+    int end_bit           = sizeof(KeyT) * 8,
+    const stream_env& env = {})
+  {
+    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+      return SortKeysDescending(t, b, d_keys_in, d_keys_out, num_items, begin_bit, end_bit, s);
+    });
+  }
+
+  template <typename KeyT, typename NumItemsT, std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  [[nodiscard]] static cudaError_t SortKeysDescending(
+    DoubleBuffer<KeyT>& d_keys,
+    NumItemsT num_items,
+    int begin_bit         = 0,
+    int end_bit           = sizeof(KeyT) * 8,
+    const stream_env& env = {})
+  {
+    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+      return SortKeysDescending(t, b, d_keys, num_items, begin_bit, end_bit, s);
+    });
+  }
+};
+
+} // namespace cub

@@ -1,0 +1,189 @@
+// thrust::sort / stable_sort / sort_by_key / stable_sort_by_key for arithmetic keys in device memory, on top of
+// libb200rs.so -- the cases the reference's CUDA backend routes to radix sort
+// (/root/reference/thrust/thrust/system/cuda/detail/sort.h:288-339, __smart_sort::can_use_primitive_sort: arithmetic
+// key + thrust::less / thrust::greater [or cuda::std::less/greater]).  Public entry points being mirrored:
+// /root/reference/thrust/thrust/sort.h (sort :212, stable_sort :404, sort_by_key :589, stable_sort_by_key :804 and the
+// execution-policy overloads next to them).
+//
+// Every call is ONE b200rs_sort_inplace (include/b200rs.h): scratch from the stream-ordered pool, DoubleBuffer sort,
+// copy-back iff needed, synchronise (the reference synchronises unless the policy is par_nosync,
+// sort.h:260 `synchronize_optional`).  A non-zero return throws thrust::system_error like the reference
+// (sort.h:260-262).  No other backend exists here: host iterators or non-arithmetic keys are compile errors.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "../b200rs.h"
+#include "device_vector.h"
+
+namespace thrust
+{
+
+template <class T = void>
+struct less
+{};
+template <class T = void>
+struct greater
+{};
+
+// Execution policies: thrust::device, thrust::cuda::par.on(stream), thrust::cuda::par_nosync.on(stream)
+namespace cuda
+{
+struct execute_on_stream
+{
+  cudaStream_t stream = nullptr;
+  bool sync           = true;
+};
+struct par_t : execute_on_stream
+{
+  execute_on_stream on(cudaStream_t s) const
+  {
+    return execute_on_stream{s, sync};
+  }
+};
+static const par_t par{};
+static const par_t par_nosync{{nullptr, false}};
+} // namespace cuda
+static const cuda::par_t device{};
+
+namespace detail
+{
+template <class K>
+constexpr int key_kind_of()
+{
+  static_assert(std::is_arithmetic<K>::value, "thrust::sort shim: arithmetic keys only (radix-sort path)");
+  return std::is_floating_point<K>::value ? B200RS_KEY_FLOAT
+       : (std::is_signed<K>::value && !std::is_same<K, bool>::value) ? B200RS_KEY_INT
+                                                                     : B200RS_KEY_UINT;
+}
+template <class T>
+T* unwrap(device_ptr<T> it)
+{
+  return it.get();
+}
+template <class T>
+T* unwrap(T* it)
+{
+  return it;
+}
+template <class C>
+struct is_descending : std::false_type
+{};
+template <class T>
+struct is_descending<greater<T>> : std::true_type
+{};
+
+template <class KeyIt, class Compare>
+void radix_sort_keys(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Compare)
+{
+  auto* k = unwrap(first);
+  using K = std::remove_pointer_t<decltype(k)>;
+  const int rc = b200rs_sort_inplace(k, nullptr, static_cast<uint64_t>(unwrap(last) - k), key_kind_of<K>(),
+                                     int(sizeof(K)), 0, is_descending<Compare>::value ? 1 : 0, pol.sync ? 1 : 0,
+                                     reinterpret_cast<b200rs_stream_t>(pol.stream));
+  throw_on_error(static_cast<cudaError_t>(rc), "radix_sort: failed on 2nd step"); // sort.h:261
+}
+template <class KeyIt, class ValIt, class Compare>
+void radix_sort_pairs(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values, Compare)
+{
+  auto* k = unwrap(first);
+  auto* v = unwrap(values);
+  using K = std::remove_pointer_t<decltype(k)>;
+  using V = std::remove_pointer_t<decltype(v)>;
+  static_assert(std::is_trivially_copyable<V>::value, "values are moved as opaque blobs");
+  static_assert(sizeof(V) == 1 || sizeof(V) == 2 || sizeof(V) == 4 || sizeof(V) == 8 || sizeof(V) == 16,
+                "value width must be 1/2/4/8/16 bytes");
+  const int rc = b200rs_sort_inplace(k, v, static_cast<uint64_t>(unwrap(last) - k), key_kind_of<K>(), int(sizeof(K)),
+                                     int(sizeof(V)), is_descending<Compare>::value ? 1 : 0, pol.sync ? 1 : 0,
+                                     reinterpret_cast<b200rs_stream_t>(pol.stream));
+  throw_on_error(static_cast<cudaError_t>(rc), "radix_sort: failed on 2nd step");
+}
+} // namespace detail
+
+// ---- sort / stable_sort (radix sort is stable, so both names are the same call, as in the reference)
+template <class KeyIt>
+void sort(KeyIt first, KeyIt last)
+{
+  detail::radix_sort_keys(device, first, last, less<>{});
+}
+template <class KeyIt, class T, template <class> class Cmp>
+void sort(KeyIt first, KeyIt last, Cmp<T> comp)
+{
+  detail::radix_sort_keys(device, first, last, comp);
+}
+template <class KeyIt>
+void sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last)
+{
+  detail::radix_sort_keys(pol, first, last, less<>{});
+}
+template <class KeyIt, class T, template <class> class Cmp>
+void sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Cmp<T> comp)
+{
+  detail::radix_sort_keys(pol, first, last, comp);
+}
+template <class KeyIt>
+void stable_sort(KeyIt first, KeyIt last)
+{
+  detail::radix_sort_keys(device, first, last, less<>{});
+}
+template <class KeyIt, class T, template <class> class Cmp>
+void stable_sort(KeyIt first, KeyIt last, Cmp<T> comp)
+{
+  detail::radix_sort_keys(device, first, last, comp);
+}
+template <class KeyIt>
+void stable_sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last)
+{
+  detail::radix_sort_keys(pol, first, last, less<>{});
+}
+template <class KeyIt, class T, template <class> class Cmp>
+void stable_sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Cmp<T> comp)
+{
+  detail::radix_sort_keys(pol, first, last, comp);
+}
+
+// ---- sort_by_key / stable_sort_by_key
+template <class KeyIt, class ValIt>
+void sort_by_key(KeyIt first, KeyIt last, ValIt values)
+{
+  detail::radix_sort_pairs(device, first, last, values, less<>{});
+}
+template <class KeyIt, class ValIt, class T, template <class> class Cmp>
+void sort_by_key(KeyIt first, KeyIt last, ValIt values, Cmp<T> comp)
+{
+  detail::radix_sort_pairs(device, first, last, values, comp);
+}
+template <class KeyIt, class ValIt>
+void sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values)
+{
+  detail::radix_sort_pairs(pol, first, last, values, less<>{});
+}
+template <class KeyIt, class ValIt, class T, template <class> class Cmp>
+void sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values, Cmp<T> comp)
+{
+  detail::radix_sort_pairs(pol, first, last, values, comp);
+}
+template <class KeyIt, class ValIt>
+void stable_sort_by_key(KeyIt first, KeyIt last, ValIt values)
+{
+  detail::radix_sort_pairs(device, first, last, values, less<>{});
+}
+template <class KeyIt, class ValIt, class T, template <class> class Cmp>
+void stable_sort_by_key(KeyIt first, KeyIt last, ValIt values, Cmp<T> comp)
+{
+  detail::radix_sort_pairs(device, first, last, values, comp);
+}
+template <class KeyIt, class ValIt>
+void stable_sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values)
+{
+  detail::radix_sort_pairs(pol, first, last, values, less<>{});
+}
+template <class KeyIt, class ValIt, class T, template <class> class Cmp>
+void stable_sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values, Cmp<T> comp)
+{
+  detail::radix_sort_pairs(pol, first, last, values, comp);
+}
+
+} // namespace thrust

@@ -1,0 +1,370 @@
+// GPU test program for the cub::DeviceRadixSort header shim (include/cub/device/device_radix_sort.cuh).
+// Mirrors the reference's own API tests: the env-API golden vectors of
+// /root/reference/cub/test/catch2_test_device_radix_sort_env_api.cu:84-136 and the shape of
+// catch2_test_device_radix_sort_{keys,pairs}.cu (pointer + DoubleBuffer, descending, bit windows, stream, stability),
+// checked on the host against std::stable_sort over the bit-ordered key (the helper the reference tests use,
+// catch2_radix_sort_helper.cuh:174-312).  Run by tests/test_cxx_shims.py under `pytest -m gpu`; exit code 0 == pass.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <vector>
+
+static int g_failed = 0;
+#define REQUIRE(cond)                                                     \
+  do                                                                      \
+  {                                                                       \
+    if (!(cond))                                                          \
+    {                                                                     \
+      printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);            \
+      ++g_failed;                                                         \
+    }                                                                     \
+  } while (0)
+
+template <class T>
+struct dev
+{
+  T* p = nullptr;
+  size_t n;
+  explicit dev(size_t n_)
+      : n(n_)
+  {
+    cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+  }
+  explicit dev(const std::vector<T>& h)
+      : dev(h.size())
+  {
+    cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  ~dev()
+  {
+    cudaFree(p);
+  }
+  std::vector<T> host() const
+  {
+    std::vector<T> h(n);
+    cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost);
+    return h;
+  }
+};
+
+// order-preserving unsigned image of a key (Traits<T>::TwiddleIn, util_type.cuh:857-963)
+template <class K>
+uint64_t ordered_bits(K k)
+{
+  using U = std::conditional_t<sizeof(K) == 1, uint8_t,
+            std::conditional_t<sizeof(K) == 2, uint16_t, std::conditional_t<sizeof(K) == 4, uint32_t, uint64_t>>>;
+  U u;
+  std::memcpy(&u, &k, sizeof(K));
+  const U high = U(1) << (sizeof(K) * 8 - 1);
+  if (std::is_floating_point<K>::value)
+  {
+    u = (u & high) ? U(~u) : U(u ^ high);
+  }
+  else if (std::is_signed<K>::value)
+  {
+    u ^= high;
+  }
+  return u;
+}
+
+// Largest N the reference sorts with its single-CTA kernel on sm_100 (dispatch_radix_sort.cuh:1980, policy
+// tuning_radix_sort.cuh:1747,1833-1841 scaled by util_arch.cuh:128-138).  Only the float-zero rule depends on it.
+inline size_t reference_single_tile_items(int key_bytes, int value_bytes)
+{
+  int dom     = std::max(std::max(key_bytes, value_bytes), 4);
+  int items   = std::max(19 * 4 / dom, 1);
+  int threads = std::min((48 * 1024 / (dom * items) + 31) / 32 * 32, 256);
+  return size_t(threads) * size_t(items);
+}
+
+template <class K>
+std::vector<uint32_t>
+expected_permutation(const std::vector<K>& keys, bool desc, int begin_bit, int end_bit, int value_bytes = 0)
+{
+  std::vector<uint32_t> perm(keys.size());
+  std::iota(perm.begin(), perm.end(), 0u);
+  const int kbits     = int(sizeof(K)) * 8;
+  const uint64_t all  = kbits == 64 ? ~0ull : ((1ull << kbits) - 1);
+  const uint64_t high = 1ull << (kbits - 1);
+  const int nbits     = end_bit - begin_bit;
+  const uint64_t mask = nbits >= 64 ? ~0ull : ((1ull << nbits) - 1);
+  const bool single   = keys.size() <= reference_single_tile_items(int(sizeof(K)), value_bytes);
+  auto digit          = [&](uint32_t i) {
+    uint64_t b = ordered_bits(keys[i]);
+    if (desc)
+    {
+      b = ~b & all; // descending == ascending on the inverted bit image (radix_rank_sort_operations.cuh:533-573)
+    }
+    if (std::is_floating_point<K>::value)
+    {
+      // -0.0 == +0.0 (radix_rank_sort_operations.cuh:44-82): the onesweep path replaces the pattern 0x7f..f by
+      // 0x80..0 in the (possibly inverted) key domain; the single-tile kernel applies the rule before inverting.
+      if (desc && single)
+      {
+        b = b == high ? (~high & all) : b;
+      }
+      else
+      {
+        b = b == (~high & all) ? high : b;
+      }
+    }
+    return (b >> begin_bit) & mask;
+  };
+  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return digit(a) < digit(b); });
+  return perm;
+}
+
+template <class K>
+std::vector<K> random_keys(size_t n, unsigned seed, int and_rounds = 1)
+{
+  std::mt19937_64 rng(seed);
+  std::vector<K> k(n);
+  for (auto& x : k)
+  {
+    uint64_t r = rng();
+    for (int i = 1; i < and_rounds; ++i)
+    {
+      r &= rng();
+    }
+    if (std::is_floating_point<K>::value)
+    {
+      // finite values, some zeros of both signs
+      const int e = int(r % 41) - 20;
+      double v    = double(int64_t(r >> 20) % 2000001 - 1000000) * std::ldexp(1.0, e);
+      x           = K(v);
+      if (r % 97 == 0) x = K(0.0);
+      if (r % 89 == 0) x = K(-0.0);
+    }
+    else
+    {
+      std::memcpy(&x, &r, sizeof(K));
+    }
+  }
+  return k;
+}
+
+template <class K>
+bool same_bits(const std::vector<K>& a, const std::vector<K>& b)
+{
+  return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(K)) == 0);
+}
+
+template <class K, class V>
+void check_pairs(size_t n, bool desc, int begin_bit, int end_bit, bool double_buffer, cudaStream_t stream, int and_rounds)
+{
+  auto hk = random_keys<K>(n, 1234 + unsigned(n), and_rounds);
+  std::vector<V> hv(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    hv[i] = V(i);
+  }
+  auto perm = expected_permutation(hk, desc, begin_bit, end_bit, int(sizeof(V)));
+  std::vector<K> ek(n);
+  std::vector<V> ev(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    ek[i] = hk[perm[i]];
+    ev[i] = hv[perm[i]];
+  }
+  dev<K> k0(hk), k1(n);
+  dev<V> v0(hv), v1(n);
+  size_t bytes = 0;
+  void* tmp    = nullptr;
+  cudaError_t e;
+  if (double_buffer)
+  {
+    cub::DoubleBuffer<K> dk(k0.p, k1.p);
+    cub::DoubleBuffer<V> dv(v0.p, v1.p);
+    e = desc ? cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, dk, dv, n, begin_bit, end_bit, stream)
+             : cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, n, begin_bit, end_bit, stream);
+    REQUIRE(e == cudaSuccess);
+    REQUIRE(dk.selector == 0); // the size query must not touch the selector
+    cudaMalloc(&tmp, bytes);
+    e = desc ? cub::DeviceRadixSort::SortPairsDescending(tmp, bytes, dk, dv, n, begin_bit, end_bit, stream)
+             : cub::DeviceRadixSort::SortPairs(tmp, bytes, dk, dv, n, begin_bit, end_bit, stream);
+    REQUIRE(e == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    REQUIRE(dk.selector == dv.selector);
+    std::vector<K> gk(n);
+    std::vector<V> gv(n);
+    cudaMemcpy(gk.data(), dk.Current(), n * sizeof(K), cudaMemcpyDeviceToHost);
+    cudaMemcpy(gv.data(), dv.Current(), n * sizeof(V), cudaMemcpyDeviceToHost);
+    REQUIRE(same_bits(gk, ek));
+    REQUIRE(same_bits(gv, ev));
+  }
+  else
+  {
+    e = desc ? cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, k0.p, k1.p, v0.p, v1.p, n, begin_bit, end_bit,
+                                                         stream)
+             : cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, v1.p, n, begin_bit, end_bit, stream);
+    REQUIRE(e == cudaSuccess);
+    cudaMalloc(&tmp, bytes);
+    e = desc ? cub::DeviceRadixSort::SortPairsDescending(tmp, bytes, k0.p, k1.p, v0.p, v1.p, n, begin_bit, end_bit,
+                                                         stream)
+             : cub::DeviceRadixSort::SortPairs(tmp, bytes, k0.p, k1.p, v0.p, v1.p, n, begin_bit, end_bit, stream);
+    REQUIRE(e == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    REQUIRE(same_bits(k1.host(), ek));
+    REQUIRE(same_bits(v1.host(), ev));
+    REQUIRE(same_bits(k0.host(), hk)); // the pointer API never writes its input (device_radix_sort.cuh:310)
+    REQUIRE(same_bits(v0.host(), hv));
+  }
+  cudaFree(tmp);
+}
+
+template <class K>
+void check_keys(size_t n, bool desc, int begin_bit, int end_bit, bool double_buffer, cudaStream_t stream)
+{
+  auto hk   = random_keys<K>(n, 99 + unsigned(n));
+  auto perm = expected_permutation(hk, desc, begin_bit, end_bit);
+  std::vector<K> ek(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    ek[i] = hk[perm[i]];
+  }
+  dev<K> k0(hk), k1(n);
+  size_t bytes = 0;
+  void* tmp    = nullptr;
+  cudaError_t e;
+  if (double_buffer)
+  {
+    cub::DoubleBuffer<K> dk(k0.p, k1.p);
+    e = desc ? cub::DeviceRadixSort::SortKeysDescending(nullptr, bytes, dk, n, begin_bit, end_bit, stream)
+             : cub::DeviceRadixSort::SortKeys(nullptr, bytes, dk, n, begin_bit, end_bit, stream);
+    REQUIRE(e == cudaSuccess);
+    cudaMalloc(&tmp, bytes);
+    e = desc ? cub::DeviceRadixSort::SortKeysDescending(tmp, bytes, dk, n, begin_bit, end_bit, stream)
+             : cub::DeviceRadixSort::SortKeys(tmp, bytes, dk, n, begin_bit, end_bit, stream);
+    REQUIRE(e == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    std::vector<K> gk(n);
+    cudaMemcpy(gk.data(), dk.Current(), n * sizeof(K), cudaMemcpyDeviceToHost);
+    REQUIRE(same_bits(gk, ek));
+  }
+  else
+  {
+    e = desc ? cub::DeviceRadixSort::SortKeysDescending(nullptr, bytes, k0.p, k1.p, n, begin_bit, end_bit, stream)
+             : cub::DeviceRadixSort::SortKeys(nullptr, bytes, k0.p, k1.p, n, begin_bit, end_bit, stream);
+    REQUIRE(e == cudaSuccess);
+    cudaMalloc(&tmp, bytes);
+    e = desc ? cub::DeviceRadixSort::SortKeysDescending(tmp, bytes, k0.p, k1.p, n, begin_bit, end_bit, stream)
+             : cub::DeviceRadixSort::SortKeys(tmp, bytes, k0.p, k1.p, n, begin_bit, end_bit, stream);
+    REQUIRE(e == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    REQUIRE(same_bits(k1.host(), ek));
+    REQUIRE(same_bits(k0.host(), hk));
+  }
+  cudaFree(tmp);
+}
+
+// the reference's documented examples (catch2_test_device_radix_sort_env_api.cu:84-136 and the keys variants)
+void env_api_goldens()
+{
+  const std::vector<int> keys{8, 6, 7, 5, 3, 0, 9}, vals{0, 1, 2, 3, 4, 5, 6};
+  {
+    dev<int> ki(keys), ko(7), vi(vals), vo(7);
+    auto error = cub::DeviceRadixSort::SortPairs(ki.p, ko.p, vi.p, vo.p, static_cast<int>(keys.size()));
+    cudaDeviceSynchronize();
+    REQUIRE(error == cudaSuccess);
+    REQUIRE((ko.host() == std::vector<int>{0, 3, 5, 6, 7, 8, 9}));
+    REQUIRE((vo.host() == std::vector<int>{5, 4, 3, 1, 2, 0, 6}));
+  }
+  {
+    dev<int> ki(keys), ko(7), vi(vals), vo(7);
+    auto error = cub::DeviceRadixSort::SortPairsDescending(ki.p, ko.p, vi.p, vo.p, static_cast<int>(keys.size()));
+    cudaDeviceSynchronize();
+    REQUIRE(error == cudaSuccess);
+    REQUIRE((ko.host() == std::vector<int>{9, 8, 7, 6, 5, 3, 0}));
+    REQUIRE((vo.host() == std::vector<int>{6, 0, 2, 1, 3, 4, 5}));
+  }
+  {
+    dev<int> ki(keys), ko(7);
+    auto error = cub::DeviceRadixSort::SortKeys(ki.p, ko.p, static_cast<int>(keys.size()));
+    cudaDeviceSynchronize();
+    REQUIRE(error == cudaSuccess);
+    REQUIRE((ko.host() == std::vector<int>{0, 3, 5, 6, 7, 8, 9}));
+  }
+  {
+    dev<int> ki(keys), ko(7);
+    cudaStream_t s;
+    cudaStreamCreate(&s);
+    auto error =
+      cub::DeviceRadixSort::SortKeysDescending(ki.p, ko.p, static_cast<int>(keys.size()), 0, 32, cub::stream_env{s});
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    REQUIRE(error == cudaSuccess);
+    REQUIRE((ko.host() == std::vector<int>{9, 8, 7, 6, 5, 3, 0}));
+  }
+  {
+    dev<int> a(keys), b(7), va(vals), vb(7);
+    cub::DoubleBuffer<int> dk(a.p, b.p), dv(va.p, vb.p);
+    auto error = cub::DeviceRadixSort::SortPairs(dk, dv, 7);
+    cudaDeviceSynchronize();
+    REQUIRE(error == cudaSuccess);
+    std::vector<int> gk(7), gv(7);
+    cudaMemcpy(gk.data(), dk.Current(), 28, cudaMemcpyDeviceToHost);
+    cudaMemcpy(gv.data(), dv.Current(), 28, cudaMemcpyDeviceToHost);
+    REQUIRE((gk == std::vector<int>{0, 3, 5, 6, 7, 8, 9}));
+    REQUIRE((gv == std::vector<int>{5, 4, 3, 1, 2, 0, 6}));
+  }
+}
+
+void edge_cases()
+{
+  // empty input: success, temp size >= 1, nothing touched (dispatch_radix_sort.cuh:1950-1977)
+  size_t bytes = 0;
+  auto e       = cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const uint32_t*) nullptr, (uint32_t*) nullptr, 0);
+  REQUIRE(e == cudaSuccess);
+  REQUIRE(bytes >= 1);
+  // temp blob too small -> cudaErrorInvalidValue (util_temporary_storage.cuh:75-78)
+  dev<uint32_t> a(1 << 16), b(1 << 16);
+  bytes = 0;
+  e     = cub::DeviceRadixSort::SortKeys(nullptr, bytes, a.p, b.p, 1 << 16);
+  REQUIRE(e == cudaSuccess);
+  size_t too_small = bytes / 2;
+  void* tmp;
+  cudaMalloc(&tmp, bytes);
+  e = cub::DeviceRadixSort::SortKeys(tmp, too_small, a.p, b.p, 1 << 16);
+  REQUIRE(e == cudaErrorInvalidValue);
+  cudaFree(tmp);
+  // begin_bit == end_bit: a copy (dispatch_radix_sort.cuh:1364-1410)
+  check_keys<uint32_t>(10000, false, 7, 7, false, nullptr);
+  check_keys<uint32_t>(10000, true, 7, 7, true, nullptr);
+}
+
+int main()
+{
+  cudaStream_t stream;
+  cudaStreamCreate(&stream);
+  env_api_goldens();
+  edge_cases();
+  const size_t sizes[] = {1, 2, 255, 4864, 4865, 100000, (1u << 21) + 17};
+  for (size_t n : sizes)
+  {
+    check_keys<uint32_t>(n, false, 0, 32, false, stream);
+    check_keys<int32_t>(n, true, 0, 32, true, stream);
+    check_keys<float>(n, true, 8, 24, false, nullptr);
+    check_keys<int64_t>(n, true, 16, 48, false, stream);
+    check_keys<double>(n, false, 0, 64, true, stream);
+    check_keys<uint8_t>(n, false, 0, 8, false, stream);
+    check_keys<int16_t>(n, true, 3, 11, true, stream);
+    check_pairs<uint64_t, uint32_t>(n, false, 0, 64, false, stream, 1);
+    check_pairs<uint64_t, uint32_t>(n, false, 0, 64, true, stream, 5); // low entropy: many ties, stability visible
+    check_pairs<uint32_t, uint32_t>(n, true, 0, 32, true, stream, 3);
+    check_pairs<float, uint64_t>(n, false, 0, 32, false, stream, 1);
+    check_pairs<uint8_t, uint16_t>(n, false, 0, 8, true, stream, 1);
+    check_pairs<int32_t, uint8_t>(n, true, 5, 20, false, stream, 1);
+  }
+  cudaStreamDestroy(stream);
+  if (g_failed == 0)
+  {
+    printf("test_cub_shim: all checks passed\n");
+  }
+  return g_failed == 0 ? 0 : 1;
+}
