@@ -17,6 +17,8 @@ struct OnesweepConfig
   int tile_items;
   size_t smem_bytes;
   onesweep_launch_fn launch;
+  int bulk_store; // 1: TMA bulk-store kernel (onesweep_tma.cuh); needs 16-byte aligned output pointers
+  int opt;        // OnesweepOpt bits of the classic kernel
 };
 
 // index 0 is the default for the (key_bytes, value_bytes) combination

@@ -104,6 +104,42 @@ static const OnesweepConfig* pick_config(int key_bytes, int value_bytes)
   return tab + idx;
 }
 
+// the classic kernel used when a bulk-store configuration meets output pointers that are not 16-byte aligned
+static const OnesweepConfig* fallback_config(int key_bytes, int value_bytes)
+{
+  int count                 = 0;
+  const OnesweepConfig* tab = configs_for(key_bytes, value_bytes, &count);
+  for (int i = 0; tab != nullptr && i < count; ++i)
+  {
+    if (!tab[i].bulk_store)
+    {
+      return tab + i;
+    }
+  }
+  return nullptr;
+}
+
+struct PortionPlan
+{
+  uint64_t tile, portion_items, portions, max_tiles;
+};
+
+static PortionPlan plan_portions(uint64_t num_items, uint64_t tile)
+{
+  PortionPlan p;
+  p.tile                    = tile;
+  uint64_t portion_cap      = (uint64_t(1) << 30) - 1;
+  const uint64_t portion_ov = g_portion_override.load(std::memory_order_relaxed);
+  if (portion_ov != 0 && portion_ov < portion_cap)
+  {
+    portion_cap = portion_ov;
+  }
+  p.portion_items = (portion_cap / tile > 0 ? portion_cap / tile : 1) * tile;
+  p.portions      = (num_items + p.portion_items - 1) / p.portion_items;
+  p.max_tiles     = ((num_items < p.portion_items ? num_items : p.portion_items) + tile - 1) / tile;
+  return p;
+}
+
 static int sm_count_of_current_device(int* out)
 {
   static std::atomic<int> cache[64];
@@ -199,8 +235,8 @@ int b200rs_describe_config(int key_bytes, int value_bytes, int config_index, cha
   if (buf != nullptr && buf_len > 0)
   {
     const OnesweepConfig& c = tab[config_index];
-    snprintf(buf, buf_len, "k%dv%d threads=%d items=%d minb=%d tile=%d smem=%zu", key_bytes, value_bytes, c.threads,
-             c.items_per_thread, c.min_blocks, c.tile_items, c.smem_bytes);
+    snprintf(buf, buf_len, "k%dv%d threads=%d items=%d minb=%d tile=%d smem=%zu opt=%d%s", key_bytes, value_bytes,
+             c.threads, c.items_per_thread, c.min_blocks, c.tile_items, c.smem_bytes, c.opt, c.bulk_store ? " tma" : "");
   }
   return count;
 }
@@ -367,17 +403,39 @@ int b200rs_sort(
   {
     return int(cudaErrorNotSupported);
   }
-  const int passes          = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
-  const uint64_t tile       = uint64_t(cfg->tile_items);
-  uint64_t portion_cap      = (uint64_t(1) << 30) - 1;
-  const uint64_t portion_ov = g_portion_override.load(std::memory_order_relaxed);
-  if (portion_ov != 0 && portion_ov < portion_cap)
+  const int passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+  // A bulk-store configuration needs 16-byte aligned destinations; otherwise the classic kernel runs.  The temp blob
+  // is sized for whichever of the two needs more, so the size query does not depend on the pointers.
+  const OnesweepConfig* fb = cfg->bulk_store ? fallback_config(key_bytes, value_bytes) : nullptr;
+  if (cfg->bulk_store && fb == nullptr)
   {
-    portion_cap = portion_ov;
+    return int(cudaErrorNotSupported);
   }
-  const uint64_t portion_items = (portion_cap / tile > 0 ? portion_cap / tile : 1) * tile;
-  const uint64_t portions      = (num_items + portion_items - 1) / portion_items;
-  const uint64_t max_tiles     = ((num_items < portion_items ? num_items : portion_items) + tile - 1) / tile;
+  PortionPlan plan       = plan_portions(num_items, uint64_t(cfg->tile_items));
+  uint64_t size_portions = plan.portions;
+  uint64_t size_tiles    = plan.max_tiles;
+  if (fb != nullptr)
+  {
+    const PortionPlan alt = plan_portions(num_items, uint64_t(fb->tile_items));
+    size_portions         = alt.portions > size_portions ? alt.portions : size_portions;
+    size_tiles            = alt.max_tiles > size_tiles ? alt.max_tiles : size_tiles;
+    if (!query)
+    {
+      size_t bits = reinterpret_cast<size_t>(d_keys_out) | reinterpret_cast<size_t>(d_values_out);
+      if (overwrite)
+      {
+        bits |= reinterpret_cast<size_t>(d_keys_in) | reinterpret_cast<size_t>(d_values_in);
+      }
+      if (bits % 16 != 0)
+      {
+        cfg  = fb;
+        plan = alt;
+      }
+    }
+  }
+  const uint64_t tile          = plan.tile;
+  const uint64_t portion_items = plan.portion_items;
+  const uint64_t portions      = plan.portions;
   const bool need_tmp          = !overwrite && passes > 1;
 
   // temp blob: every sub-allocation 256-byte aligned, +255 so an unaligned blob can be aligned up
@@ -385,14 +443,14 @@ int b200rs_sort(
   TempLayout L;
   size_t off = 0;
   L.off_bins = off;
-  off += align_up(size_t(portions) * passes * RADIX * sizeof(unsigned long long), 256);
+  off += align_up(size_t(size_portions) * passes * RADIX * sizeof(unsigned long long), 256);
   L.off_ctrs = off;
-  off += align_up(size_t(portions) * passes * sizeof(uint32_t), 256);
+  off += align_up(size_t(size_portions) * passes * sizeof(uint32_t), 256);
   L.off_lb0 = off;
-  off += align_up(size_t(max_tiles) * RADIX * sizeof(uint32_t), 256);
+  off += align_up(size_t(size_tiles) * RADIX * sizeof(uint32_t), 256);
   L.control_bytes = off;
   L.off_lb1       = off;
-  off += align_up(size_t(max_tiles) * RADIX * sizeof(uint32_t), 256);
+  off += align_up(size_t(size_tiles) * RADIX * sizeof(uint32_t), 256);
   L.off_keys = off;
   off += need_tmp ? align_up(size_t(num_items) * key_bytes, 256) : 0;
   L.off_vals = off;

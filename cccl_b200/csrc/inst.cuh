@@ -4,27 +4,28 @@
 
 #include "configs.h"
 #include "onesweep.cuh"
+#include "onesweep_tma.cuh"
 
 namespace b200rs
 {
 
-template <class U, int VB, int NT, int IPT, int RANK, int MINB = 1>
+template <class U, int VB, int NT, int IPT, int RANK, int MINB = 1, int OPT = 0>
 cudaError_t launch_onesweep(const PassArgs& args, unsigned grid, cudaStream_t stream)
 {
-  using L = OnesweepSmem<U, VB, NT, IPT>;
+  using L = OnesweepSmem<U, VB, NT, IPT, OPT>;
   // the -0.0 == +0.0 digit rule is compiled in only where it can matter: floating-point keys (4/8 bytes);
   // 64-bit output offsets only for arrays of 2^32 items and more
   constexpr bool CAN_FLOAT = sizeof(U) >= 4;
   const bool flt           = CAN_FLOAT && args.xf.float_mask != 0;
-  auto kernel              = onesweep_kernel<U, VB, NT, IPT, RANK, MINB, false, false>;
+  auto kernel              = onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, false, false>;
   if (args.big)
   {
-    kernel = flt ? onesweep_kernel<U, VB, NT, IPT, RANK, MINB, CAN_FLOAT, true>
-                 : onesweep_kernel<U, VB, NT, IPT, RANK, MINB, false, true>;
+    kernel = flt ? onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, CAN_FLOAT, true>
+                 : onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, false, true>;
   }
   else if (flt)
   {
-    kernel = onesweep_kernel<U, VB, NT, IPT, RANK, MINB, CAN_FLOAT, false>;
+    kernel = onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, CAN_FLOAT, false>;
   }
   if (L::BYTES > 48 * 1024)
   {
@@ -39,11 +40,42 @@ cudaError_t launch_onesweep(const PassArgs& args, unsigned grid, cudaStream_t st
   return cudaPeekAtLastError();
 }
 
-template <class U, int VB, int NT, int IPT, int RANK, int MINB = 1>
+template <class U, int VB, int NT, int IPT, int RANK, int MINB = 1, int OPT = 0>
 constexpr OnesweepConfig make_config()
 {
-  return OnesweepConfig{NT, IPT, RANK, MINB, NT * IPT, OnesweepSmem<U, VB, NT, IPT>::BYTES,
-                        &launch_onesweep<U, VB, NT, IPT, RANK, MINB>};
+  return OnesweepConfig{NT, IPT, RANK, MINB, NT * IPT, OnesweepSmem<U, VB, NT, IPT, OPT>::BYTES,
+                        &launch_onesweep<U, VB, NT, IPT, RANK, MINB, OPT>, 0, OPT};
+}
+
+// TMA bulk-store variant (onesweep_tma.cuh); LBW = look-back window
+template <class U, int VB, int NT, int IPT, int MINB, int LBW>
+cudaError_t launch_onesweep_tma(const PassArgs& args, unsigned grid, cudaStream_t stream)
+{
+  using L = TmaSmem<U, VB, NT, IPT>;
+  constexpr bool CAN_FLOAT = sizeof(U) >= 4;
+  const bool flt           = CAN_FLOAT && args.xf.float_mask != 0;
+  auto kernel              = onesweep_tma_kernel<U, VB, NT, IPT, MINB, LBW, false>;
+  if (flt)
+  {
+    kernel = onesweep_tma_kernel<U, VB, NT, IPT, MINB, LBW, CAN_FLOAT>;
+  }
+  if (L::BYTES > 48 * 1024)
+  {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::BYTES));
+    if (e != cudaSuccess)
+    {
+      return e;
+    }
+  }
+  kernel<<<grid, NT, L::BYTES, stream>>>(args);
+  return cudaPeekAtLastError();
+}
+
+template <class U, int VB, int NT, int IPT, int MINB, int LBW = 4>
+constexpr OnesweepConfig make_tma_config()
+{
+  return OnesweepConfig{NT, IPT, RANK_BALLOT, MINB, NT * IPT, TmaSmem<U, VB, NT, IPT>::BYTES,
+                        &launch_onesweep_tma<U, VB, NT, IPT, MINB, LBW>, 1, 0};
 }
 
 } // namespace b200rs

@@ -1,27 +1,36 @@
-// onesweep instantiations for 1-byte keys.  Index 0 of each table is the default configuration.
+// onesweep instantiations for 1-byte keys.  Index 0 of each table is the default configuration; the others are kept
+// for A/B measurement (tools/sweep.py) and are all covered by the parity tests.
 #include "inst.cuh"
 
 namespace b200rs
 {
 using K = uint8_t;
 #define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
+#define O(VB, NT, IPT, MINB, OPT) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB, OPT>()
+#define T(VB, NT, IPT, MINB, LBW) make_tma_config<K, VB, NT, IPT, MINB, LBW>()
 
 static const OnesweepConfig cfg_v0[] = {
+  O(0, 256, 32, 3, 7),
   C(0, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v1[] = {
+  O(1, 256, 32, 3, 7),
   C(1, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v2[] = {
+  O(2, 256, 32, 3, 7),
   C(2, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v4[] = {
+  O(4, 256, 32, 3, 7),
   C(4, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v8[] = {
+  O(8, 256, 20, 3, 7),
   C(8, 256, 20, 3)
 };
 static const OnesweepConfig cfg_v16[] = {
+  O(16, 256, 12, 3, 7),
   C(16, 256, 12, 3)
 };
 

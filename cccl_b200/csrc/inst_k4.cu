@@ -1,35 +1,45 @@
-// onesweep instantiations for 4-byte keys (u32 / i32 / f32).  Index 0 of each table is the default configuration.
+// onesweep instantiations for 4-byte keys (u32 / i32 / f32).  Index 0 of each table is the default configuration; the others are kept
+// for A/B measurement (tools/sweep.py) and are all covered by the parity tests.
 #include "inst.cuh"
 
 namespace b200rs
 {
 using K = uint32_t;
 #define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
+#define O(VB, NT, IPT, MINB, OPT) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB, OPT>()
+#define T(VB, NT, IPT, MINB, LBW) make_tma_config<K, VB, NT, IPT, MINB, LBW>()
 
 static const OnesweepConfig cfg_v0[] = {
+  O(0, 256, 40, 3, 7),
   C(0, 256, 32, 4),
-  C(0, 256, 40, 3),
-  C(0, 512, 24, 2),
-  make_config<K, 0, 512, 16, RANK_MATCH, 2>() // MATCH.ANY, kept for measurement
+  O(0, 256, 32, 4, 7),
+  O(0, 256, 36, 3, 7),
+  O(0, 256, 44, 3, 7),
+  O(0, 256, 48, 3, 7),
+  T(0, 512, 32, 2, 4)
 };
 static const OnesweepConfig cfg_v1[] = {
+  O(1, 256, 32, 3, 7),
   C(1, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v2[] = {
+  O(2, 256, 32, 3, 7),
   C(2, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v4[] = {
+  O(4, 256, 36, 3, 7),
   C(4, 256, 36, 3),
-  C(4, 256, 32, 3),
-  C(4, 512, 20, 2)
+  O(4, 256, 32, 3, 7),
+  O(4, 256, 24, 4, 7),
+  T(4, 256, 24, 3, 4)
 };
 static const OnesweepConfig cfg_v8[] = {
-  C(8, 256, 20, 3),
-  C(8, 512, 12, 2)
+  O(8, 256, 20, 3, 7),
+  C(8, 256, 20, 3)
 };
 static const OnesweepConfig cfg_v16[] = {
-  C(16, 256, 12, 3),
-  C(16, 512, 8, 2)
+  O(16, 256, 12, 3, 7),
+  C(16, 256, 12, 3)
 };
 
 #define B200RS_TABLE(arr)                     \

@@ -1,34 +1,43 @@
-// onesweep instantiations for 8-byte keys (u64 / i64 / f64).  Index 0 of each table is the default configuration.
+// onesweep instantiations for 8-byte keys (u64 / i64 / f64).  Index 0 of each table is the default configuration; the others are kept
+// for A/B measurement (tools/sweep.py) and are all covered by the parity tests.
 #include "inst.cuh"
 
 namespace b200rs
 {
 using K = uint64_t;
 #define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
+#define O(VB, NT, IPT, MINB, OPT) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB, OPT>()
+#define T(VB, NT, IPT, MINB, LBW) make_tma_config<K, VB, NT, IPT, MINB, LBW>()
 
 static const OnesweepConfig cfg_v0[] = {
+  O(0, 256, 24, 3, 7),
   C(0, 256, 24, 3),
-  C(0, 256, 32, 2),
-  C(0, 512, 16, 2)
+  O(0, 256, 32, 2, 7),
+  O(0, 256, 16, 4, 7),
+  T(0, 256, 24, 3, 4)
 };
 static const OnesweepConfig cfg_v1[] = {
+  O(1, 256, 24, 3, 7),
   C(1, 256, 24, 3)
 };
 static const OnesweepConfig cfg_v2[] = {
+  O(2, 256, 24, 3, 7),
   C(2, 256, 24, 3)
 };
 static const OnesweepConfig cfg_v4[] = {
+  O(4, 256, 20, 3, 7),
   C(4, 256, 24, 3),
-  C(4, 256, 20, 3),
-  C(4, 512, 14, 2)
+  O(4, 256, 24, 3, 7),
+  O(4, 256, 16, 4, 7),
+  T(4, 256, 14, 3, 4)
 };
 static const OnesweepConfig cfg_v8[] = {
-  C(8, 256, 16, 3),
-  C(8, 512, 12, 2)
+  O(8, 256, 16, 3, 7),
+  C(8, 256, 16, 3)
 };
 static const OnesweepConfig cfg_v16[] = {
-  C(16, 256, 10, 3),
-  C(16, 512, 8, 2)
+  O(16, 256, 10, 3, 7),
+  C(16, 256, 10, 3)
 };
 
 #define B200RS_TABLE(arr)                     \

@@ -40,14 +40,23 @@ enum RankAlgo
   RANK_BALLOT = 1
 };
 
-template <class U, int VBYTES, int NT, int IPT>
+// Optimisation switches of the kernel (template parameter OPT), kept switchable so each one can be measured alone.
+enum OnesweepOpt
+{
+  OPT_FMA_NOT   = 1, // per-lane ballot complement as a predicated IMAD (FMA pipe) instead of LOP3 (ALU pipe)
+  OPT_LB_WINDOW = 2, // look-back polls 8 predecessors per round trip
+  OPT_CTR16     = 4  // 16-bit warp counters: half the words per bank, fewer shared-memory bank conflicts
+};
+
+template <class U, int VBYTES, int NT, int IPT, int OPT = 0>
 struct OnesweepSmem
 {
   static constexpr int NW          = NT / 32;
   static constexpr int TILE        = NT * IPT;
   static constexpr int ITEM_BYTES  = int(sizeof(U)) > VBYTES ? int(sizeof(U)) : VBYTES;
-  static constexpr uint32_t OFF_WARP = 0;                             // u32 [NW][256] running offsets
-  static constexpr uint32_t OFF_GOFF = OFF_WARP + NW * RADIX * 4;     // u64 [256] per-digit output offsets
+  static constexpr int CTR_BYTES   = (OPT & OPT_CTR16) ? 2 : 4;
+  static constexpr uint32_t OFF_WARP = 0;                             // u32/u16 [NW][256] running offsets
+  static constexpr uint32_t OFF_GOFF = OFF_WARP + NW * RADIX * CTR_BYTES; // u64 [256] per-digit output offsets
   static constexpr uint32_t OFF_MISC = OFF_GOFF + RADIX * 8;          // u32 [16]
   static constexpr uint32_t OFF_DATA = OFF_MISC + 64;                 // staged tile (16-byte aligned)
   static constexpr size_t BYTES      = size_t(OFF_DATA) + size_t(TILE) * ITEM_BYTES;
@@ -214,14 +223,127 @@ __device__ __forceinline__ uint32_t pass_digit(U key, int shift, uint32_t mask, 
   return uint32_t(key >> shift) & mask;
 }
 
+// warp counters: 32-bit, or 16-bit (OPT_CTR16: two digits per word, so a warp-wide access touches at most four
+// distinct words per bank instead of eight)
+template <bool C16>
+__device__ __forceinline__ uint32_t ctr_ld(uint32_t addr)
+{
+  uint32_t v;
+  if (C16)
+  {
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  }
+  else
+  {
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  }
+  return v;
+}
+template <bool C16>
+__device__ __forceinline__ void ctr_st(uint32_t addr, uint32_t v)
+{
+  if (C16)
+  {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  }
+  else
+  {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  }
+}
+
+// match-by-ballot with the per-lane complement on the FMA pipe: `ones` is 0xffffffff passed at run time so that ptxas
+// keeps x * ones + ones (== ~x) as an IMAD instead of folding it back into a LOP3.
+__device__ __forceinline__ void match_digit_ballot_fma(uint32_t d, uint32_t ones, uint32_t& b, uint32_t& c)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p0, p1, p2, p3;\n"
+    ".reg .b32 v0, v1, v2, v3, v4, v5, v6, v7, t, dh;\n"
+    "shr.u32 dh, %2, 4;\n"
+    "and.b32 t, %2, 1; setp.ne.u32 p0, t, 0;\n"
+    "and.b32 t, %2, 2; setp.ne.u32 p1, t, 0;\n"
+    "and.b32 t, %2, 4; setp.ne.u32 p2, t, 0;\n"
+    "and.b32 t, %2, 8; setp.ne.u32 p3, t, 0;\n"
+    "vote.sync.ballot.b32 v0, p0, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v1, p1, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v2, p2, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v3, p3, 0xffffffff;\n"
+    "@!p0 mad.lo.u32 v0, v0, %3, %3;\n"
+    "@!p1 mad.lo.u32 v1, v1, %3, %3;\n"
+    "@!p2 mad.lo.u32 v2, v2, %3, %3;\n"
+    "@!p3 mad.lo.u32 v3, v3, %3, %3;\n"
+    "and.b32 t, dh, 1; setp.ne.u32 p0, t, 0;\n"
+    "and.b32 t, dh, 2; setp.ne.u32 p1, t, 0;\n"
+    "and.b32 t, dh, 4; setp.ne.u32 p2, t, 0;\n"
+    "and.b32 t, dh, 8; setp.ne.u32 p3, t, 0;\n"
+    "vote.sync.ballot.b32 v4, p0, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v5, p1, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v6, p2, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v7, p3, 0xffffffff;\n"
+    "@!p0 mad.lo.u32 v4, v4, %3, %3;\n"
+    "@!p1 mad.lo.u32 v5, v5, %3, %3;\n"
+    "@!p2 mad.lo.u32 v6, v6, %3, %3;\n"
+    "@!p3 mad.lo.u32 v7, v7, %3, %3;\n"
+    "lop3.b32 t, v0, v1, v2, 0x80;\n"
+    "lop3.b32 %0, v3, v4, v5, 0x80;\n"
+    "lop3.b32 %1, v6, v7, t, 0x80;\n"
+    "}\n"
+    : "=r"(b), "=r"(c)
+    : "r"(d), "r"(ones));
+}
+
+// Decoupled look-back of one digit over the predecessor tiles (status words `base[t * RADIX]`, t < tile), W words per
+// round trip.  Each word carries its own flags, so the loads need no ordering among themselves.
+template <int W>
+__device__ __forceinline__ uint32_t lookback_prefix(const uint32_t* base, uint32_t tile)
+{
+  uint32_t prefix = 0;
+  int t           = int(tile) - 1;
+  while (true)
+  {
+    uint32_t w[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+    {
+      w[j] = (t - j >= 0) ? ld_relaxed_u32(base + size_t(t - j) * RADIX) : LB_INCLUSIVE;
+    }
+    int state = 0, used = 0; // 0 consuming, 1 met a word that is not published yet, 2 reached an inclusive prefix
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+    {
+      if (state == 0)
+      {
+        if ((w[j] & LB_FLAG_MASK) == 0)
+        {
+          state = 1;
+        }
+        else
+        {
+          prefix += w[j] & LB_VALUE_MASK;
+          ++used;
+          state = (w[j] & LB_INCLUSIVE) ? 2 : 0;
+        }
+      }
+    }
+    if (state == 2)
+    {
+      return prefix;
+    }
+    t -= used;
+  }
+}
+
 // The tile body.  FULL: every item of the tile is valid (all tiles but possibly the last one of a portion).
-template <class U, int VBYTES, int NT, int IPT, int RANK, bool FLOATK, bool BIG, bool FULL>
+template <class U, int VBYTES, int NT, int IPT, int RANK, int OPT, bool FLOATK, bool BIG, bool FULL>
 __device__ __forceinline__ void onesweep_tile(
   const PassArgs& a, const uint32_t sbase, const uint32_t tile, const uint32_t tile_base, const uint32_t valid)
 {
-  using L = OnesweepSmem<U, VBYTES, NT, IPT>;
+  using L = OnesweepSmem<U, VBYTES, NT, IPT, OPT>;
   using V = typename value_of<VBYTES>::type;
-  constexpr int NW = L::NW;
+  constexpr int NW       = L::NW;
+  constexpr bool C16     = (OPT & OPT_CTR16) != 0;
+  constexpr uint32_t CB  = L::CTR_BYTES;
 
   const uint32_t tid   = threadIdx.x;
   const uint32_t lane  = tid & 31;
@@ -234,7 +356,7 @@ __device__ __forceinline__ void onesweep_tile(
   const uint32_t s_goff = sbase + L::OFF_GOFF;
   const uint32_t s_misc = sbase + L::OFF_MISC;
   const uint32_t s_data = sbase + L::OFF_DATA;
-  const uint32_t s_mine = s_warp + warp * (RADIX * 4); // this warp's running offsets
+  const uint32_t s_mine = s_warp + warp * (RADIX * CB); // this warp's running offsets
 
   // ---- load keys, warp-striped
   U key[IPT];
@@ -268,9 +390,10 @@ __device__ __forceinline__ void onesweep_tile(
     }
   }
 
-  // ---- rank: warp-private running digit offsets; afterwards the warp's row holds its digit histogram
-  // staged positions, two 16-bit values per register.  Besides halving the registers, the PRMT packing stops ptxas
-  // from keeping BOTH addends of every rank alive (it otherwise fuses the add into the later IADD3 and spills).
+  // ---- rank: warp-private running digit counts; afterwards the warp's row holds its digit histogram.
+  // rank2 keeps (position of the key among the warp's keys of its digit) + 1, two 16-bit values per register: the +1 is
+  // the value the group leader stores anyway, and it is undone for free by staging at s_data - one item.  Besides
+  // halving the registers, the PRMT packing stops ptxas from keeping BOTH addends of every rank alive.
   uint32_t rank2[(IPT + 1) / 2];
   const uint32_t lt_mask = lanemask_lt();
   const uint32_t gt_mask = lanemask_gt();
@@ -283,18 +406,22 @@ __device__ __forceinline__ void onesweep_tile(
     {
       b = c = __match_any_sync(0xffffffffu, d);
     }
+    else if (OPT & OPT_FMA_NOT)
+    {
+      match_digit_ballot_fma(d, a.all_ones, b, c);
+    }
     else
     {
       match_digit_ballot(d, b, c);
     }
     const uint32_t before = __popc(b & c & lt_mask);
-    const uint32_t ctr    = s_mine + d * 4;
-    const uint32_t off    = lds32(ctr);
-    if ((b & c & gt_mask) == 0) // highest peer lane: its `before` + 1 is the group size
+    const uint32_t ctr    = s_mine + d * CB;
+    const uint32_t next   = ctr_ld<C16>(ctr) + before + 1;
+    if ((b & c & gt_mask) == 0) // highest peer lane: its position + 1 is the new running count
     {
-      sts32(ctr, off + before + 1);
+      ctr_st<C16>(ctr, next);
     }
-    put16(rank2, i, off + before);
+    put16(rank2, i, next);
   }
   __syncthreads();
 
@@ -306,7 +433,7 @@ __device__ __forceinline__ void onesweep_tile(
 #pragma unroll
     for (int w = 0; w < NW; ++w)
     {
-      total += lds32(s_warp + (w * RADIX + tid) * 4);
+      total += ctr_ld<C16>(s_warp + (w * RADIX + tid) * CB);
     }
     st_relaxed_u32(lb_word, (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | total);
     uint32_t incl = total;
@@ -338,25 +465,25 @@ __device__ __forceinline__ void onesweep_tile(
 #pragma unroll
     for (int w = 0; w < NW; ++w)
     {
-      const uint32_t addr = s_warp + (w * RADIX + tid) * 4;
-      const uint32_t c    = lds32(addr);
-      sts32(addr, run);
+      const uint32_t addr = s_warp + (w * RADIX + tid) * CB;
+      const uint32_t c    = ctr_ld<C16>(addr);
+      ctr_st<C16>(addr, run);
       run += c;
     }
   }
   __syncthreads();
 
-  // ---- stage keys in shared memory in digit order
+  // ---- stage keys in shared memory in digit order (ranks are + 1: stage one item below s_data)
 #pragma unroll
   for (int i = 0; i < IPT; ++i)
   {
     const uint32_t d = pass_digit<FLOATK>(key[i], shift, dmask, neg_zero, pos_zero);
-    const uint32_t r = get16(rank2, i) + lds32(s_mine + d * 4);
+    const uint32_t r = get16(rank2, i) + ctr_ld<C16>(s_mine + d * CB);
     if (VBYTES > 0)
     {
       update16(rank2, i, r);
     }
-    sts_t<U>(s_data + r * uint32_t(sizeof(U)), key[i]);
+    sts_t<U>(s_data - uint32_t(sizeof(U)) + r * uint32_t(sizeof(U)), key[i]);
   }
 
   // values are fetched now so their latency hides behind the look-back
@@ -380,20 +507,27 @@ __device__ __forceinline__ void onesweep_tile(
     uint32_t prefix = 0;
     if (tile > 0)
     {
-      const uint32_t* w = lb_word - RADIX;
-      while (true)
+      if (OPT & OPT_LB_WINDOW)
       {
-        const uint32_t s = ld_relaxed_u32(w);
-        if ((s & LB_FLAG_MASK) == 0)
+        prefix = lookback_prefix<8>(a.lookback + tid, tile);
+      }
+      else
+      {
+        const uint32_t* w = lb_word - RADIX;
+        while (true)
         {
-          continue; // predecessor has started (dynamic tile ids) but not published yet
+          const uint32_t s = ld_relaxed_u32(w);
+          if ((s & LB_FLAG_MASK) == 0)
+          {
+            continue; // predecessor has started (dynamic tile ids) but not published yet
+          }
+          prefix += s & LB_VALUE_MASK;
+          if (s & LB_INCLUSIVE)
+          {
+            break;
+          }
+          w -= RADIX;
         }
-        prefix += s & LB_VALUE_MASK;
-        if (s & LB_INCLUSIVE)
-        {
-          break;
-        }
-        w -= RADIX;
       }
       st_relaxed_u32(lb_word, LB_INCLUSIVE | (prefix + total));
     }
@@ -410,13 +544,6 @@ __device__ __forceinline__ void onesweep_tile(
     if (a.bins_next != nullptr && tile_base + valid == a.num_items)
     {
       a.bins_next[tid] = gbase + total;
-    }
-    if (a.lookback_next != nullptr)
-    {
-      for (uint32_t t = tile; t < a.lookback_next_tiles; t += gridDim.x)
-      {
-        a.lookback_next[size_t(t) * RADIX + tid] = 0;
-      }
     }
   }
   __syncthreads();
@@ -473,7 +600,7 @@ __device__ __forceinline__ void onesweep_tile(
     {
       if (FULL || chunk + i * 32 < valid)
       {
-        sts_t<V>(s_data + get16(rank2, i) * uint32_t(sizeof(V)), val[i]);
+        sts_t<V>(s_data - uint32_t(sizeof(V)) + get16(rank2, i) * uint32_t(sizeof(V)), val[i]);
       }
     }
     __syncthreads();
@@ -497,15 +624,24 @@ __device__ __forceinline__ void onesweep_tile(
       }
     }
   }
+
+  // the chained-scan status words of the NEXT launch are zeroed by this one, off the critical path
+  if (tid < RADIX && a.lookback_next != nullptr)
+  {
+    for (uint32_t t = tile; t < a.lookback_next_tiles; t += gridDim.x)
+    {
+      a.lookback_next[size_t(t) * RADIX + tid] = 0;
+    }
+  }
 }
 
-template <class U, int VBYTES, int NT, int IPT, int RANK, int MINB, bool FLOATK, bool BIG>
+template <class U, int VBYTES, int NT, int IPT, int RANK, int MINB, int OPT, bool FLOATK, bool BIG>
 __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
 {
-  using L = OnesweepSmem<U, VBYTES, NT, IPT>;
+  using L = OnesweepSmem<U, VBYTES, NT, IPT, OPT>;
   constexpr int TILE = L::TILE;
   static_assert(NT >= RADIX && NT % 32 == 0, "one thread per digit is required");
-  static_assert(TILE <= 65536, "staged positions are kept in 16 bits");
+  static_assert(TILE < 65536, "staged positions (+1) are kept in 16 bits");
 
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
@@ -517,12 +653,14 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
     sts32(sbase + L::OFF_MISC + 32, atomicAdd(a.tile_counter, 1u));
   }
   {
-    const uint32_t row = sbase + L::OFF_WARP + (tid >> 5) * (RADIX * 4) + (tid & 31) * 4;
+    // zero the warp counters: NW * 256 counters of CTR_BYTES each, as 32-bit words
+    constexpr int WORDS = L::NW * RADIX * L::CTR_BYTES / 4;
 #pragma unroll
-    for (int j = 0; j < RADIX / 32; ++j)
+    for (int j = 0; j < WORDS / NT; ++j)
     {
-      sts32(row + j * 128, 0);
+      sts32(sbase + L::OFF_WARP + (j * NT + tid) * 4, 0);
     }
+    static_assert(WORDS % NT == 0, "counter words must divide evenly over the threads");
   }
   __syncthreads();
   const uint32_t tile      = lds32(sbase + L::OFF_MISC + 32);
@@ -530,11 +668,11 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
   const uint32_t valid     = min(uint32_t(TILE), a.num_items - tile_base);
   if (valid == uint32_t(TILE))
   {
-    onesweep_tile<U, VBYTES, NT, IPT, RANK, FLOATK, BIG, true>(a, sbase, tile, tile_base, valid);
+    onesweep_tile<U, VBYTES, NT, IPT, RANK, OPT, FLOATK, BIG, true>(a, sbase, tile, tile_base, valid);
   }
   else
   {
-    onesweep_tile<U, VBYTES, NT, IPT, RANK, FLOATK, BIG, false>(a, sbase, tile, tile_base, valid);
+    onesweep_tile<U, VBYTES, NT, IPT, RANK, OPT, FLOATK, BIG, false>(a, sbase, tile, tile_base, valid);
   }
 }
 
