@@ -14,8 +14,6 @@ static const OnesweepConfig cfg_v0[] = {
   C(0, 256, 32, 4),
   O(0, 256, 32, 4, 7),
   O(0, 256, 36, 3, 7),
-  O(0, 256, 44, 3, 7),
-  O(0, 256, 48, 3, 7),
   T(0, 512, 32, 2, 4)
 };
 static const OnesweepConfig cfg_v1[] = {
@@ -30,7 +28,6 @@ static const OnesweepConfig cfg_v4[] = {
   O(4, 256, 36, 3, 7),
   C(4, 256, 36, 3),
   O(4, 256, 32, 3, 7),
-  O(4, 256, 24, 4, 7),
   T(4, 256, 24, 3, 4)
 };
 static const OnesweepConfig cfg_v8[] = {

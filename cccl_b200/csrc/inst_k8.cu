@@ -13,7 +13,6 @@ static const OnesweepConfig cfg_v0[] = {
   O(0, 256, 24, 3, 7),
   C(0, 256, 24, 3),
   O(0, 256, 32, 2, 7),
-  O(0, 256, 16, 4, 7),
   T(0, 256, 24, 3, 4)
 };
 static const OnesweepConfig cfg_v1[] = {
@@ -28,7 +27,6 @@ static const OnesweepConfig cfg_v4[] = {
   O(4, 256, 20, 3, 7),
   C(4, 256, 24, 3),
   O(4, 256, 24, 3, 7),
-  O(4, 256, 16, 4, 7),
   T(4, 256, 14, 3, 4)
 };
 static const OnesweepConfig cfg_v8[] = {
