@@ -19,6 +19,8 @@ EXPORTS = (
     "b200rs_sort_inplace",
     "b200rs_digit_histogram",
     "b200rs_splitter_ranks",
+    "b200rs_select_histogram",
+    "b200rs_bucket_ids",
     "b200rs_last_launch_count",
     "b200rs_set_config",
     "b200rs_set_portion_items",
@@ -59,6 +61,10 @@ def lib() -> ctypes.CDLL:
         l.b200rs_digit_histogram.argtypes = [vp, u64, i32, i32, i32, i32, i32, vp, vp]
         l.b200rs_splitter_ranks.restype = i32
         l.b200rs_splitter_ranks.argtypes = [vp, u64, i32, i32, i32, vp, i32, vp, vp, vp]
+        l.b200rs_select_histogram.restype = i32
+        l.b200rs_select_histogram.argtypes = [vp, u64, i32, i32, i32, ctypes.POINTER(u64), i32, i32, vp, vp]
+        l.b200rs_bucket_ids.restype = i32
+        l.b200rs_bucket_ids.argtypes = [vp, u64, i32, i32, i32, ctypes.POINTER(u64), i32, vp, vp]
         l.b200rs_last_launch_count.restype = i32
         l.b200rs_last_launch_count.argtypes = []
         l.b200rs_set_config.restype = i32

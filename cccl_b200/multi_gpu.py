@@ -8,7 +8,21 @@ for bit; rank r's output has exactly as many items as its input.  The reference'
 keys-only and unstable; its protocol (local sort -> splitters by global counting -> all-to-all -> local merge/sort,
 hss/histogramming.h:522-610, hss/data_exchange.h:380-450) is what this restates for radix keys, with EXACT splitters.
 
-Protocol
+Protocol "partition" (default; SURVEY.md 8e as written: histogram rounds -> partition by destination -> exchange ->
+ONE local sort)
+  1. exact splitters by MSD radix select over the UNSORTED shard: per round one 256-bin histogram of the next digit
+     among the keys carrying each candidate prefix (round 0: the upsweep histogram kernel; later rounds
+     b200rs_select_histogram), one all-reduce, the bin holding the target rank is kept; key_bytes rounds.  The local
+     counts below / equal to each splitter fall out of the same rounds;
+  2. destination buckets (b200rs_bucket_ids: keys strictly between two splitters and keys tied with a splitter get
+     separate buckets) and ONE stable partition pass by bucket (the 1-byte-key SortPairs path, <= 5 bits): every
+     destination's items are then contiguous, in local order.  Ties of a splitter key are split by (source rank, local
+     position), so partitions are exact for any duplicates and stability is kept;
+  3. key/value exchange: direct NVLink peer copies into the destination's receive buffer (torch symmetric memory)
+     when available, else all-to-all-v over NCCL; receive buffer in source-rank order;
+  4. ONE local stable sort of the received items (source-rank order + stable sort == global stable order).
+
+Protocol "sort" (the first implementation, kept selectable and tested)
   1. local stable sort of the shard (b200rs_sort, DoubleBuffer form);
   2. exact splitters by MSD radix select over the bit-ordered key space: per round every rank binary-searches 257 bin
      boundaries per splitter in its SORTED shard (b200rs_splitter_ranks), one all-reduce sums the counts, the bin
@@ -99,7 +113,129 @@ class CudaOps:
         return out[:m], out[m:]
 
 
+    # ---- primitives of the partition-first protocol
+    def top_digit_histogram(self, keys, descending):
+        """(1, 256) int64: histogram of the most significant 8-bit digit of the bit-ordered keys (upsweep kernel)."""
+        import torch
+
+        kdt = _torch_np_dtype(keys)
+        out = torch.empty(RADIX, dtype=torch.int64, device=keys.device)
+        bits = kdt.itemsize * 8
+        rc = self.lib.b200rs_digit_histogram(
+            keys.data_ptr() if keys.numel() else 0, keys.numel(), key_kind_of(kdt), kdt.itemsize, bits - RADIX_BITS,
+            bits, int(bool(descending)), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "b200rs_digit_histogram")
+        return out.view(1, RADIX)
+
+    def select_histogram(self, keys, prefixes: np.ndarray, rnd: int, descending):
+        """(len(prefixes), 256) int64: per candidate prefix, histogram of digit `rnd` (MSD first) of the keys whose
+        higher digits equal the prefix."""
+        import ctypes
+
+        import torch
+
+        kdt = _torch_np_dtype(keys)
+        m = int(prefixes.size)
+        out = torch.empty((m, RADIX), dtype=torch.int64, device=keys.device)
+        arr = (ctypes.c_uint64 * max(m, 1))(*[int(x) for x in prefixes])
+        rc = self.lib.b200rs_select_histogram(
+            keys.data_ptr() if keys.numel() else 0, keys.numel(), key_kind_of(kdt), kdt.itemsize,
+            int(bool(descending)), arr, m, rnd, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "b200rs_select_histogram")
+        return out
+
+    def bucket_ids(self, keys, splitters: np.ndarray, descending):
+        """uint8 tensor: 2 * #{splitters below the key} + [key equals a splitter] (bit-ordered domain)."""
+        import ctypes
+
+        import torch
+
+        kdt = _torch_np_dtype(keys)
+        m = int(splitters.size)
+        ids = torch.empty(keys.numel(), dtype=torch.uint8, device=keys.device)
+        arr = (ctypes.c_uint64 * max(m, 1))(*[int(x) for x in splitters])
+        rc = self.lib.b200rs_bucket_ids(
+            keys.data_ptr() if keys.numel() else 0, keys.numel(), key_kind_of(kdt), kdt.itemsize,
+            int(bool(descending)), arr, m, ids.data_ptr() if keys.numel() else 0,
+            torch.cuda.current_stream().cuda_stream)
+        _native.check(rc, "b200rs_bucket_ids")
+        return ids
+
+    def partition(self, ids, nbits, keys, values):
+        """Stable partition of (keys, values) by the bucket id of each item: one radix pass over the low `nbits` bits
+        of the 1-byte ids with the payload as the value (b200rs_sort, pointer form)."""
+        import torch
+
+        from .radix_sort import SortOrder, radix_sort
+
+        n = ids.numel()
+        outs = []
+        ids_out = torch.empty_like(ids)
+        for payload in (keys, values):
+            if payload is None:
+                outs.append(None)
+                continue
+            out = torch.empty_like(payload)
+            if n:
+                view = getattr(torch, _A2A_VIEW[payload.element_size()])
+                keep = radix_sort(d_in_keys=ids, d_out_keys=ids_out, d_in_values=payload.view(view),
+                                  d_out_values=out.view(view), num_items=n, order=SortOrder.ASCENDING, begin_bit=0,
+                                  end_bit=max(int(nbits), 1))
+                del keep
+            outs.append(out)
+        return outs[0], outs[1]
+
+
 # ----------------------------------------------------------------------------------------------- splitter selection
+def select_splitters_unsorted(keys, targets, *, kind, key_bytes, descending, ops, group, dist, stats=None):
+    """Exact splitters from the UNSORTED shard.  For every global target rank t finds the bit-ordered value x of the
+    t-th smallest key of the whole job by MSD radix select, and returns (bounds, splitters): bounds[(world, nt)] =
+    number of items of each source rank that go to ranks <= the target's, counted in the order "bucket id, then local
+    position"; splitters = the distinct x values, ascending (uint64)."""
+    import torch
+
+    world = dist.get_world_size(group)
+    nt = len(targets)
+    if nt == 0:
+        return np.zeros((world, 0), dtype=np.int64), np.zeros(0, dtype=np.uint64)
+    tgt = np.maximum(np.asarray(targets, dtype=np.int64), 1)
+    prefix = np.zeros(nt, dtype=np.uint64)
+    below = np.zeros(nt, dtype=np.int64)     # global count of keys whose high digits are below the prefix
+    lt_local = np.zeros(nt, dtype=np.int64)  # the same, for this rank's shard only
+    eq_local = np.zeros(nt, dtype=np.int64)
+    for rnd in range(key_bytes):
+        uniq, inv = np.unique(prefix, return_inverse=True)
+        if rnd == 0:
+            h_local = ops.top_digit_histogram(keys, descending)
+        else:
+            h_local = ops.select_histogram(keys, uniq, rnd, descending)
+        h_glob = h_local.clone()
+        _all_reduce(dist, h_glob, group)
+        both = torch.stack([h_local, h_glob]).cpu().numpy()  # (2, len(uniq), 256)
+        for i in range(nt):
+            hl, hg = both[0, inv[i]], both[1, inv[i]]
+            cum = np.cumsum(hg)
+            b = min(int(np.searchsorted(cum, tgt[i] - below[i], side="left")), RADIX - 1)
+            if b > 0:
+                below[i] += int(cum[b - 1])
+                lt_local[i] += int(hl[:b].sum())
+            eq_local[i] = int(hl[b])
+            prefix[i] = (prefix[i] << np.uint64(RADIX_BITS)) + np.uint64(b)
+    mine = torch.from_numpy(np.stack([lt_local, eq_local])).to(keys.device)
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    _all_gather(dist, allc, mine, group)
+    allc = torch.stack(allc).cpu().numpy()  # (world, 2, nt)
+    lt_all, eq_all = allc[:, 0, :], allc[:, 1, :]
+    need = np.asarray(targets, dtype=np.int64) - lt_all.sum(axis=0)  # items EQUAL to the splitter that go to lower ranks
+    before = np.cumsum(eq_all, axis=0) - eq_all
+    take = np.clip(need[None, :] - before, 0, eq_all)
+    if stats is not None:
+        stats["splitter_rounds"] = key_bytes
+        stats["splitters_bit_ordered"] = [int(x) for x in prefix]
+    assert (take.sum(axis=0) == np.clip(need, 0, None)).all(), "splitter selection is inconsistent"
+    return lt_all + take, np.unique(prefix)
+
+
 def select_splitters(sorted_keys, targets, *, kind, key_bytes, descending, ops, group, dist, stats=None):
     """For every global target rank t (number of items that must end up on lower ranks) find the bit-ordered splitter
     value x = the (t)-th smallest key of the whole job (1-based; t == 0 gives x = 0), and return, per target, this
@@ -179,13 +315,83 @@ class _Phases:
                 for i in range(len(self.marks) - 1)}
 
 
-def distributed_sort(keys, values=None, *, descending=False, group=None, ops=None, stats=None):
+class _PeerBuffers:
+    """Receive buffers every rank of the group can write directly over NVLink (torch symmetric memory: CUDA VMM
+    allocations mapped into every peer).  One byte buffer per payload (keys, values), grown on demand, cached per
+    (group, device) because the rendezvous is a collective that costs milliseconds."""
+
+    _cache = {}
+
+    def __init__(self, nbytes, device, group, dist):
+        import torch
+        import torch.distributed._symmetric_memory as symm
+
+        self.nbytes = int(nbytes)
+        self.world = dist.get_world_size(group)
+        self.bufs, self.hdls, self.peers = [], [], []
+        for _ in range(2):
+            buf = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
+            hdl = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            self.bufs.append(buf)
+            self.hdls.append(hdl)
+            self.peers.append([hdl.get_buffer(r, (self.nbytes,), torch.uint8, 0) for r in range(self.world)])
+
+    @classmethod
+    def get(cls, nbytes, device, group, dist):
+        key = (id(group), str(device))
+        cur = cls._cache.get(key)
+        if cur is None or cur.nbytes < nbytes:
+            cls._cache[key] = cur = cls(max(int(nbytes), 1 << 20), device, group, dist)
+        return cur
+
+
+def _peer_exchange(dist, group, rank, edges, payloads, n_local, max_local):
+    """Every rank copies each destination's contiguous segment straight into that destination's receive buffer
+    (cudaMemcpyAsync device-to-peer over NVLink, in stream order), then a device-side barrier; the receive buffer is
+    laid out in source-rank order.  Returns views of this rank's receive buffers."""
+    world = edges.shape[0]
+    item = max(p.element_size() for p in payloads if p is not None)
+    pb = _PeerBuffers.get(int(max_local) * item, payloads[0].device, group, dist)
+    counts = edges[:, 1:] - edges[:, :-1]              # (source, destination)
+    dst_off = np.cumsum(counts, axis=0) - counts       # where source i's segment starts in destination r's buffer
+    pb.hdls[0].barrier(channel=0)  # every peer has finished reading its receive buffers of the previous exchange
+    outs = []
+    for which, src in enumerate(payloads):
+        if src is None:
+            outs.append(None)
+            continue
+        es = src.element_size()
+        flat = src.view(-1).view(_byte_view())
+        for step in range(world):
+            r = (rank + step) % world  # staggered so that the ranks do not all write to the same peer first
+            cnt = int(counts[rank, r])
+            if cnt == 0:
+                continue
+            lo, off = int(edges[rank, r]) * es, int(dst_off[rank, r]) * es
+            pb.peers[which][r][off:off + cnt * es].copy_(flat[lo:lo + cnt * es], non_blocking=True)
+        outs.append(pb.bufs[which][: n_local * es].view(src.dtype))
+    pb.hdls[0].barrier(channel=1)  # all sources have written their segments into this rank's buffers
+    return outs
+
+
+def _byte_view():
+    import torch
+
+    return torch.uint8
+
+
+def distributed_sort(keys, values=None, *, descending=False, group=None, ops=None, stats=None, protocol="partition",
+                     exchange="auto"):
     """Stable distributed sort of one shard per rank; returns (keys_out, values_out) with len == len(keys).
     The caller's shard is left untouched.  ``stats`` (a dict) receives splitters, exchange counts and, on CUDA, the
-    device time of each phase."""
+    device time of each phase.  ``protocol``: "partition" (histogram select -> one partition pass -> exchange -> one
+    sort) or "sort" (sort -> binary-search select -> exchange -> sort).  ``exchange``: "peer" (NVLink peer copies through
+    symmetric memory), "collective" (all-to-all-v) or "auto" (peer on CUDA + NCCL, else collective)."""
     import torch
     import torch.distributed as dist
 
+    if protocol not in ("partition", "sort"):
+        raise ValueError(f"unknown protocol {protocol!r}")
     ops = ops or CudaOps()
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -195,42 +401,71 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
     ph = _Phases(stats is not None and keys.is_cuda, torch)
     ph.mark("start")
 
-    # 1. local stable sort (the caller's shard is not modified)
-    skeys, svals = ops.sort_pairs(keys, values, descending, preserve_input=True)
-    ph.mark("local_sort")
     if world == 1:
+        out = ops.sort_pairs(keys, values, descending, preserve_input=True)
+        ph.mark("local_sort")
         if stats is not None:
             stats["phase_ms"] = ph.result()
-        return skeys, svals
+        return out
 
-    # 2. exact splitters: rank r must end with the global stable positions [sum(n[:r]), sum(n[:r+1]))
+    # rank r must end with the global stable positions [sum(n[:r]), sum(n[:r+1]))
     counts = torch.tensor([n_local], dtype=torch.int64, device=keys.device)
     allcounts = [torch.empty_like(counts) for _ in range(world)]
     _all_gather(dist, allcounts, counts, group)
     n_all = np.array([int(c.item()) for c in allcounts], dtype=np.int64)
     targets = np.cumsum(n_all)[:-1]
-    bounds = select_splitters(skeys, targets, kind=kind, key_bytes=key_bytes, descending=descending, ops=ops,
-                              group=group, dist=dist, stats=stats)
+
+    if protocol == "sort":
+        # 1. local stable sort (the caller's shard is not modified); 2. splitters by binary search in the sorted shard
+        skeys, svals = ops.sort_pairs(keys, values, descending, preserve_input=True)
+        ph.mark("local_sort")
+        bounds = select_splitters(skeys, targets, kind=kind, key_bytes=key_bytes, descending=descending, ops=ops,
+                                  group=group, dist=dist, stats=stats)
+        ph.mark("splitters")
+    else:
+        # 1. splitters by radix select over the unsorted shard; 2. one stable partition pass by destination bucket
+        if world - 1 > 15:
+            raise ValueError("the partition protocol supports up to 16 ranks (one box)")
+        bounds, splitters = select_splitters_unsorted(keys, targets, kind=kind, key_bytes=key_bytes,
+                                                      descending=descending, ops=ops, group=group, dist=dist,
+                                                      stats=stats)
+        ph.mark("splitters")
+        ids = ops.bucket_ids(keys, splitters, descending)
+        skeys, svals = ops.partition(ids, int(2 * len(splitters)).bit_length(), keys, values)
+        ph.mark("partition")
     # boundary matrix with the implicit 0 and n columns: items [edges[i, r], edges[i, r+1]) of source i go to rank r
     edges = np.concatenate([np.zeros((world, 1), dtype=np.int64), bounds, n_all[:, None]], axis=1)
     send = (edges[rank, 1:] - edges[rank, :-1]).tolist()
     recv = (edges[:, rank + 1] - edges[:, rank]).tolist()
     assert sum(recv) == n_local and min(send) >= 0 and min(recv) >= 0
-    ph.mark("splitters")
 
-    # 3. all-to-all-v, receive buffer in source-rank order
-    rkeys = torch.empty(n_local, dtype=skeys.dtype, device=skeys.device)
-    _all_to_all(dist, rkeys, skeys, recv, send, group)
-    rvals = None
-    if svals is not None:
-        rvals = torch.empty(n_local, dtype=svals.dtype, device=svals.device)
-        _all_to_all(dist, rvals, svals, recv, send, group)
+    # 3. exchange, receive buffer in source-rank order
+    use_peer = exchange == "peer" or (exchange == "auto" and keys.is_cuda and dist.get_backend(group) == "nccl")
+    peer_done = False
+    if use_peer and int(n_all.max()) > 0:
+        try:
+            rkeys, rvals = _peer_exchange(dist, group, rank, edges, [skeys, svals], n_local, int(n_all.max()))
+            peer_done = True
+        except (RuntimeError, ImportError, AttributeError) as ex:  # symmetric memory not available on this system
+            if exchange == "peer":
+                raise
+            if stats is not None:
+                stats["peer_exchange_unavailable"] = repr(ex)
+    if not peer_done:
+        rkeys = torch.empty(n_local, dtype=skeys.dtype, device=skeys.device)
+        _all_to_all(dist, rkeys, skeys, recv, send, group)
+        rvals = None
+        if svals is not None:
+            rvals = torch.empty(n_local, dtype=svals.dtype, device=svals.device)
+            _all_to_all(dist, rvals, svals, recv, send, group)
     ph.mark("exchange")
 
-    # 4. final local stable sort
-    out = ops.sort_pairs(rkeys, rvals, descending)
+    # 4. final local stable sort (peer mode: the receive buffers are shared scratch, so the result goes elsewhere)
+    out = ops.sort_pairs(rkeys, rvals, descending, preserve_input=peer_done)
     ph.mark("final_sort")
     if stats is not None:
+        stats["protocol"] = protocol
+        stats["exchange"] = "peer" if peer_done else "collective"
         stats["send_counts"] = send
         stats["recv_counts"] = recv
         item = key_bytes + (svals.element_size() if svals is not None else 0)

@@ -61,6 +61,15 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
 
+    # per-kernel device times of the final local sort of one more (untimed) step
+    lib.b200rs_timing_enable(1)
+    distributed_sort(keys, vals)
+    final_ops = {}
+    for opname, t in _native.timing_read():
+        final_ops.setdefault(opname, []).append(round(t, 4))
+    lib.b200rs_timing_enable(0)
+    barrier()
+
     # end to end: pinned host shard -> device, sort, sorted shard -> pinned host, every step
     def e2e_step():
         keys.view(torch.int32).copy_(h_keys, non_blocking=True)
@@ -93,7 +102,8 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
             assert int(a[1]) <= int(b[0]), "bench: ranks are not globally ordered"
 
     phase_ms = {k: sum(v) / len(v) for k, v in phase.items()}
-    ph = torch.tensor([phase_ms.get(k, 0.0) for k in ("local_sort", "splitters", "exchange", "final_sort")], device="cuda")
+    PH = ("splitters", "partition", "exchange", "final_sort", "local_sort")
+    ph = torch.tensor([phase_ms.get(k, 0.0) for k in PH], device="cuda")
     dist.all_reduce(ph, op=dist.ReduceOp.MAX)
     xbytes = torch.tensor([float(st.get("exchange_bytes_out", 0))], device="cuda")
     dist.all_reduce(xbytes, op=dist.ReduceOp.MAX)
@@ -102,7 +112,7 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
         total = n * world
         ex_ms = float(ph[2])
         one = 2.0 * n * 8  # bytes one onesweep pass moves per GPU
-        sort_ms = float(ph[0])
+        sort_ms = float(ph[3])
         line = {
             "metric": metric,
             "value": total / (ms * 1e-3) / 1e9,
@@ -118,16 +128,19 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
             "data": "synthetic",
             "config": {"workload": workload_name, "keys": "uint32", "values": "uint32", "pairs_per_gpu": n,
                        "total_pairs": total, "distribution": "uniform", "parallelism": f"range-partition x{world}",
-                       "exchange": "torch.distributed all_to_all_single (NCCL over NVLink 5 / NVSwitch)",
+                       "protocol": st.get("protocol"),
+                       "exchange": ("direct peer copies into symmetric-memory receive buffers over NVLink 5 / NVSwitch"
+                                    if st.get("exchange") == "peer" else
+                                    "torch.distributed all_to_all_single (NCCL over NVLink 5 / NVSwitch)"),
                        "l2_policy": "inputs (2 GiB per GPU) larger than L2; no flush needed"},
             "roofline": {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit digit pass, per GPU)",
                          "achieved": 4 * one / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else None, "peak": peak,
                          "peak_source": peak_src, "unit": "GB/s",
                          "frac": (4 * one / (sort_ms * 1e-3) / 1e9 / peak) if sort_ms > 0 else None, "traffic": None,
-                         "note": "achieved = 4 passes x 2 x N x 8 B / device time of the first local sort "
+                         "note": "achieved = 4 passes x 2 x N x 8 B / device time of the final local sort "
                                  "(histogram included in the time, not in the bytes)"},
-            "phase_ms_max_over_ranks": {"local_sort": float(ph[0]), "splitters": float(ph[1]), "exchange": ex_ms,
-                                        "final_sort": float(ph[3])},
+            "phase_ms_max_over_ranks": {k: float(ph[i]) for i, k in enumerate(PH) if float(ph[i]) > 0},
+            "final_sort_ops_ms_rank0": final_ops,
             "exchange": {"bytes_out_per_gpu": float(xbytes), "ms": ex_ms,
                          "GBps_per_direction": float(xbytes) / (ex_ms * 1e-3) / 1e9 if ex_ms > 0 else None,
                          "nvlink_peak_GBps": 770.0, "peak_source": "measured peer copy (B200_PROFILING.md)"},

@@ -162,6 +162,45 @@ B200RS_API int b200rs_splitter_ranks(
   uint64_t* d_eq,
   b200rs_stream_t stream);
 
+/*
+ * Multi-GPU support kernels of the partition-first protocol (cccl_b200/multi_gpu.py).
+ * Both work on an UNSORTED shard, in the sort's own key domain (bit-ordered value after the key transform, descending
+ * included, -0.0 viewed as +0.0), i.e. "equal" means what b200rs_sort treats as equal.
+ *
+ * b200rs_select_histogram: one round of the exact MSD radix select.  h_prefixes (HOST array, num_prefixes <= 15) holds
+ * the high digits chosen so far, as values of `round` digits (round 0: all zero).  d_hist[p * 256 + b] receives the
+ * number of local keys whose top `round` digits equal h_prefixes[p] and whose next 8-bit digit is b.  Overwritten.
+ *
+ * b200rs_bucket_ids: h_splitters (HOST array, strictly increasing bit-ordered values, num_splitters <= 15);
+ * d_ids[i] = 2 * #{j : splitter_j < key_i} + [key_i == some splitter_j]  (uint8).
+ *
+ * Replace the counting rounds and the destination computation of the reference's multi-GPU sort
+ * (/root/reference/cudax/include/cuda/experimental/__multi_gpu/algorithm/sort/hss/histogramming.h:522-610,
+ *  hss/data_exchange.h:380-450).
+ */
+B200RS_API int b200rs_select_histogram(
+  const void* d_keys,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int descending,
+  const uint64_t* h_prefixes,
+  int num_prefixes,
+  int round,
+  uint64_t* d_hist,
+  b200rs_stream_t stream);
+
+B200RS_API int b200rs_bucket_ids(
+  const void* d_keys,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int descending,
+  const uint64_t* h_splitters,
+  int num_splitters,
+  uint8_t* d_ids,
+  b200rs_stream_t stream);
+
 /* Number of kernel launches / async ops the last b200rs_sort call on this host thread enqueued
  * (bench.py's `gpu_launches`).  Thread-local. */
 B200RS_API int b200rs_last_launch_count(void);

@@ -47,7 +47,7 @@ def _host(t):
     return t.view(torch.uint8).cpu().numpy().view(dt).copy() if t.numel() else np.empty(0, dtype=dt)
 
 
-def _worker(rank, world, port, backend, results):
+def _worker(rank, world, port, backend, results, protocol="partition", exchange="auto"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     device = torch.device("cuda", rank if backend == "nccl" else 0)
@@ -70,8 +70,10 @@ def _worker(rank, world, port, backend, results):
         d_k = _dev_tensor(shards[rank], device)
         d_v = _dev_tensor(vshards[rank], device) if with_vals else None
         stats = {}
-        ok, ov = distributed_sort(d_k, d_v, descending=desc, stats=stats)
+        ok, ov = distributed_sort(d_k, d_v, descending=desc, stats=stats, protocol=protocol, exchange=exchange)
         torch.cuda.synchronize()
+        if backend == "nccl" and exchange in ("auto", "peer") and stats.get("exchange") != "peer" and sum(ns) > 0:
+            failures.append((name, "peer exchange not used: " + str(stats.get("peer_exchange_unavailable"))))
         if not np.array_equal(_host(d_k).view(np.uint8), shards[rank].view(np.uint8)):
             failures.append((name, "input shard modified"))
         allk, allv = np.concatenate(shards), np.concatenate(vshards)
@@ -95,19 +97,21 @@ def _free_port():
     return p
 
 
-def _run(world, backend):
+def _run(world, backend, protocol="partition", exchange="auto"):
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), backend, results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), backend, results, protocol, exchange), nprocs=world, join=True)
     for r in range(world):
         assert results[r] == [], f"rank {r}: {results[r]}"
 
 
+@pytest.mark.parametrize("protocol", ["partition", "sort"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_distributed_sort_cuda_ranks_sharing_one_gpu(world):
-    _run(world, "gloo")
+def test_distributed_sort_cuda_ranks_sharing_one_gpu(world, protocol):
+    _run(world, "gloo", protocol)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-def test_distributed_sort_nccl():
-    _run(min(torch.cuda.device_count(), 3), "nccl")
+@pytest.mark.parametrize("protocol,exchange", [("partition", "auto"), ("partition", "collective"), ("sort", "collective")])
+def test_distributed_sort_nccl(protocol, exchange):
+    _run(min(torch.cuda.device_count(), 3), "nccl", protocol, exchange)

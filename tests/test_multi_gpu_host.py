@@ -37,8 +37,60 @@ def to_torch(a):
     return torch.from_numpy(a.view(np.uint8).copy()).view(TDT[a.dtype]) if a.size else torch.empty(0, dtype=TDT[a.dtype])
 
 
+def _view(bits, kind, kb, descending):
+    """bit-ordered digit view, as the kernels compute it (common.cuh twiddle_in + digit_view)"""
+    b = bits.astype(np.uint64)
+    allm = np.uint64((1 << (8 * kb)) - 1)
+    high = np.uint64(1 << (8 * kb - 1))
+    if kind == 2:
+        m = np.where((b & high) != 0, allm, high)
+    elif kind == 1:
+        m = np.full_like(b, high)
+    else:
+        m = np.zeros_like(b)
+    t = (b ^ m) & allm
+    if descending:
+        t = t ^ allm
+    if kind == 2:
+        t = np.where(t == (allm ^ high), high, t)
+    return t
+
+
 class OracleOps:
-    """numpy stand-ins for the two device primitives (tests only)."""
+    """numpy stand-ins for the device primitives (tests only)."""
+
+    def _kv(self, keys, descending):
+        k = to_np(keys)
+        kb = k.dtype.itemsize
+        return _view(k.view(np.dtype(f"u{kb}")), okind(k.dtype), kb, descending), kb
+
+    def top_digit_histogram(self, keys, descending):
+        return self.select_histogram(keys, np.zeros(1, dtype=np.uint64), 0, descending)
+
+    def select_histogram(self, keys, prefixes, rnd, descending):
+        v, kb = self._kv(keys, descending)
+        lo = np.uint64(8 * kb - 8 * (rnd + 1))
+        hi = (v >> (lo + np.uint64(8))) if int(lo) + 8 < 64 else np.zeros_like(v)
+        if int(lo) + 8 >= 8 * kb:
+            hi = np.zeros_like(v)
+        dig = ((v >> lo) & np.uint64(255)).astype(np.int64)
+        out = np.zeros((len(prefixes), 256), dtype=np.int64)
+        for p, pref in enumerate(prefixes):
+            out[p] = np.bincount(dig[hi == np.uint64(pref)], minlength=256)
+        return torch.from_numpy(out)
+
+    def bucket_ids(self, keys, splitters, descending):
+        v, _ = self._kv(keys, descending)
+        ids = np.zeros(v.shape[0], dtype=np.int64)
+        for s in splitters:
+            ids += (v > np.uint64(s)).astype(np.int64) + (v >= np.uint64(s)).astype(np.int64)
+        return torch.from_numpy(ids.astype(np.uint8))
+
+    def partition(self, ids, nbits, keys, values):
+        order = np.argsort(ids.numpy() & ((1 << max(nbits, 1)) - 1), kind="stable")
+        pk = to_torch(to_np(keys)[order])
+        pv = to_torch(to_np(values)[order]) if values is not None else None
+        return pk, pv
 
     def sort_pairs(self, keys, values, descending, preserve_input=False):
         k = to_np(keys)
@@ -52,22 +104,8 @@ class OracleOps:
         kind, kb = okind(k.dtype), k.dtype.itemsize
         ut = np.dtype(f"u{kb}")
 
-        def view(bits):  # bit-ordered digit view, as the kernels compute it (common.cuh twiddle_in + digit_view)
-            b = bits.astype(np.uint64)
-            allm = np.uint64((1 << (8 * kb)) - 1)
-            high = np.uint64(1 << (8 * kb - 1))
-            if kind == 2:
-                m = np.where((b & high) != 0, allm, high)
-            elif kind == 1:
-                m = np.full_like(b, high)
-            else:
-                m = np.zeros_like(b)
-            t = (b ^ m) & allm
-            if descending:
-                t = t ^ allm
-            if kind == 2:
-                t = np.where(t == (allm ^ high), high, t)
-            return t
+        def view(bits):
+            return _view(bits, kind, kb, descending)
 
         kv = view(k.view(ut))
         pv = view(probes_bits)
@@ -93,7 +131,7 @@ CASES = [
 ]
 
 
-def _worker(rank, world, port, results):
+def _worker(rank, world, port, results, protocol="partition"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -117,7 +155,7 @@ def _worker(rank, world, port, results):
             base += n
         stats = {}
         ok, ov = distributed_sort(to_torch(shards[rank]), to_torch(vshards[rank]) if with_vals else None,
-                                  descending=desc, ops=OracleOps(), stats=stats)
+                                  descending=desc, ops=OracleOps(), stats=stats, protocol=protocol)
         allk, allv = np.concatenate(shards), np.concatenate(vshards)
         if with_vals:
             ek, ev = oracle_sort(allk, allv, descending=desc)
@@ -142,11 +180,12 @@ def _free_port():
     return p
 
 
+@pytest.mark.parametrize("protocol", ["partition", "sort"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_distributed_sort_host_logic_gloo(world):
+def test_distributed_sort_host_logic_gloo(world, protocol):
     mgr = mp.Manager()
     results = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), results, protocol), nprocs=world, join=True)
     for r in range(world):
         assert results[r] == [], f"rank {r}: {results[r]}"
 
