@@ -21,6 +21,7 @@ EXPORTS = (
     "b200rs_splitter_ranks",
     "b200rs_select_histogram",
     "b200rs_bucket_ids",
+    "b200rs_partition_by_splitters",
     "b200rs_last_launch_count",
     "b200rs_set_config",
     "b200rs_set_portion_items",
@@ -62,9 +63,12 @@ def lib() -> ctypes.CDLL:
         l.b200rs_splitter_ranks.restype = i32
         l.b200rs_splitter_ranks.argtypes = [vp, u64, i32, i32, i32, vp, i32, vp, vp, vp]
         l.b200rs_select_histogram.restype = i32
-        l.b200rs_select_histogram.argtypes = [vp, u64, i32, i32, i32, ctypes.POINTER(u64), i32, i32, vp, vp]
+        l.b200rs_select_histogram.argtypes = [vp, u64, i32, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp, u64, vp]
         l.b200rs_bucket_ids.restype = i32
         l.b200rs_bucket_ids.argtypes = [vp, u64, i32, i32, i32, ctypes.POINTER(u64), i32, vp, vp]
+        l.b200rs_partition_by_splitters.restype = i32
+        l.b200rs_partition_by_splitters.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, vp, vp, u64, i32, i32,
+                                                    i32, i32, ctypes.POINTER(u64), i32, ctypes.POINTER(u64), vp]
         l.b200rs_last_launch_count.restype = i32
         l.b200rs_last_launch_count.argtypes = []
         l.b200rs_set_config.restype = i32

@@ -229,6 +229,10 @@ struct PassArgs
   int last_pass;           // inverse transform on store
   int big;                 // whole array has >= 2^32 items: 64-bit output offsets
   KeyXform xf;
+  // bucket mode (multi-GPU partition pass): the "digit" of a key is its destination bucket against these splitters
+  // (bit-ordered values, strictly increasing): 2 * #{splitters below the key} + [key equals a splitter]
+  int num_splitters;
+  unsigned long long splitters[15];
 };
 
 } // namespace b200rs

@@ -19,6 +19,7 @@ struct OnesweepConfig
   onesweep_launch_fn launch;
   int bulk_store; // 1: TMA bulk-store kernel (onesweep_tma.cuh); needs 16-byte aligned output pointers
   int opt;        // OnesweepOpt bits of the classic kernel
+  onesweep_launch_fn launch_bucket; // the same configuration in bucket mode (OPT_BUCKET), or nullptr
 };
 
 // index 0 is the default for the (key_bytes, value_bytes) combination

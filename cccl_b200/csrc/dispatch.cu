@@ -558,6 +558,7 @@ int b200rs_sort(
       a.last_pass    = pass == passes - 1;
       a.big          = (num_items >> 32) != 0 || g_force_big.load(std::memory_order_relaxed);
       a.xf           = xf;
+      a.num_splitters = 0;
       mark_op(stream, OP_ONESWEEP);
       e = cfg->launch(a, tiles, stream);
       if (e != cudaSuccess)
@@ -574,6 +575,124 @@ int b200rs_sort(
     *selector = overwrite ? (passes & 1) : 1;
   }
   return 0;
+}
+
+int b200rs_partition_by_splitters(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int descending,
+  const uint64_t* h_splitters,
+  int num_splitters,
+  const uint64_t* h_bucket_offsets,
+  b200rs_stream_t stream_)
+{
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  t_last_launches     = 0;
+  t_events_used       = 0;
+  if (temp_storage_bytes == nullptr || key_kind < 0 || key_kind > 2 || num_splitters < 0 || num_splitters > 15
+      || (key_kind == 2 && key_bytes < 4))
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  const OnesweepConfig* cfg = nullptr;
+  {
+    int count                 = 0;
+    const OnesweepConfig* tab = configs_for(key_bytes, value_bytes, &count);
+    if (tab != nullptr && count > 0 && tab[0].launch_bucket != nullptr)
+    {
+      cfg = tab; // bucket mode is compiled for the default configuration only
+    }
+  }
+  // one launch: the chained scan carries 30-bit counts
+  if (cfg == nullptr || num_items >= (uint64_t(1) << 30))
+  {
+    return int(cudaErrorNotSupported);
+  }
+  const bool query     = d_temp_storage == nullptr;
+  const uint64_t tile  = uint64_t(cfg->tile_items);
+  const uint64_t tiles = (num_items + tile - 1) / tile;
+  size_t off           = 0;
+  const size_t off_bins = off;
+  off += align_up(RADIX * sizeof(unsigned long long), 256);
+  const size_t off_ctr = off;
+  off += 256;
+  const size_t off_lb = off;
+  off += align_up(size_t(tiles > 0 ? tiles : 1) * RADIX * sizeof(uint32_t), 256);
+  const size_t total = off + 255;
+  if (query)
+  {
+    *temp_storage_bytes = total;
+    return 0;
+  }
+  if (*temp_storage_bytes < total)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  if (num_items == 0)
+  {
+    return 0;
+  }
+  if (d_keys_in == nullptr || d_keys_out == nullptr || (value_bytes > 0 && (d_values_in == nullptr || d_values_out == nullptr))
+      || (num_splitters > 0 && h_splitters == nullptr) || h_bucket_offsets == nullptr)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  unsigned char* base = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<size_t>(d_temp_storage), 256));
+  int sms             = 0;
+  if (int e = sm_count_of_current_device(&sms))
+  {
+    return e;
+  }
+  mark_op(stream, OP_MEMSET);
+  cudaError_t e = cudaMemsetAsync(base, 0, off, stream);
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+  // exclusive bucket offsets (2 * num_splitters + 1 of them) -> the pass's per-digit output offsets
+  e = cudaMemcpyAsync(base + off_bins, h_bucket_offsets, size_t(2 * num_splitters + 1) * sizeof(uint64_t),
+                      cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+  PassArgs a;
+  a.keys_in             = d_keys_in;
+  a.keys_out            = d_keys_out;
+  a.vals_in             = value_bytes > 0 ? d_values_in : nullptr;
+  a.vals_out            = value_bytes > 0 ? d_values_out : nullptr;
+  a.lookback            = reinterpret_cast<uint32_t*>(base + off_lb);
+  a.lookback_next       = nullptr;
+  a.lookback_next_tiles = 0;
+  a.tile_counter        = reinterpret_cast<uint32_t*>(base + off_ctr);
+  a.bins                = reinterpret_cast<unsigned long long*>(base + off_bins);
+  a.bins_next           = nullptr;
+  a.num_items           = uint32_t(num_items);
+  a.num_tiles           = unsigned(tiles);
+  a.all_ones            = 0xffffffffu;
+  a.shift               = 0;
+  a.mask                = 0xffu;
+  a.first_pass          = 1;
+  a.last_pass           = 1;
+  a.big                 = 0;
+  a.xf                  = make_xform(key_kind, key_bytes, descending);
+  a.num_splitters       = num_splitters;
+  for (int i = 0; i < num_splitters; ++i)
+  {
+    a.splitters[i] = h_splitters[i];
+  }
+  mark_op(stream, OP_ONESWEEP);
+  e = cfg->launch_bucket(a, unsigned(tiles), stream);
+  mark_end(stream);
+  return int(e);
 }
 
 int b200rs_timing_enable(int on)

@@ -18,7 +18,15 @@ cudaError_t launch_onesweep(const PassArgs& args, unsigned grid, cudaStream_t st
   constexpr bool CAN_FLOAT = sizeof(U) >= 4;
   const bool flt           = CAN_FLOAT && args.xf.float_mask != 0;
   auto kernel              = onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, false, false>;
-  if (args.big)
+  if (OPT & OPT_BUCKET)
+  {
+    // one launch over < 2^30 items: no 64-bit-offset variant
+    if (flt)
+    {
+      kernel = onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, CAN_FLOAT, false>;
+    }
+  }
+  else if (args.big)
   {
     kernel = flt ? onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, CAN_FLOAT, true>
                  : onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, false, true>;
@@ -44,7 +52,16 @@ template <class U, int VB, int NT, int IPT, int RANK, int MINB = 1, int OPT = 0>
 constexpr OnesweepConfig make_config()
 {
   return OnesweepConfig{NT, IPT, RANK, MINB, NT * IPT, OnesweepSmem<U, VB, NT, IPT, OPT>::BYTES,
-                        &launch_onesweep<U, VB, NT, IPT, RANK, MINB, OPT>, 0, OPT};
+                        &launch_onesweep<U, VB, NT, IPT, RANK, MINB, OPT>, 0, OPT, nullptr};
+}
+
+// the same, plus its bucket-mode twin (multi-GPU partition pass)
+template <class U, int VB, int NT, int IPT, int RANK, int MINB = 1, int OPT = 0>
+constexpr OnesweepConfig make_config_with_bucket()
+{
+  return OnesweepConfig{NT, IPT, RANK, MINB, NT * IPT, OnesweepSmem<U, VB, NT, IPT, OPT>::BYTES,
+                        &launch_onesweep<U, VB, NT, IPT, RANK, MINB, OPT>, 0, OPT,
+                        &launch_onesweep<U, VB, NT, IPT, RANK, MINB, OPT | OPT_BUCKET>};
 }
 
 // TMA bulk-store variant (onesweep_tma.cuh); LBW = look-back window
@@ -75,7 +92,7 @@ template <class U, int VB, int NT, int IPT, int MINB, int LBW = 4>
 constexpr OnesweepConfig make_tma_config()
 {
   return OnesweepConfig{NT, IPT, RANK_BALLOT, MINB, NT * IPT, TmaSmem<U, VB, NT, IPT>::BYTES,
-                        &launch_onesweep_tma<U, VB, NT, IPT, MINB, LBW>, 1, 0};
+                        &launch_onesweep_tma<U, VB, NT, IPT, MINB, LBW>, 1, 0, nullptr};
 }
 
 } // namespace b200rs

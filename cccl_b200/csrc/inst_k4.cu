@@ -7,10 +7,11 @@ namespace b200rs
 using K = uint32_t;
 #define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
 #define O(VB, NT, IPT, MINB, OPT) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB, OPT>()
+#define OB(VB, NT, IPT, MINB, OPT) make_config_with_bucket<K, VB, NT, IPT, RANK_BALLOT, MINB, OPT>()
 #define T(VB, NT, IPT, MINB, LBW) make_tma_config<K, VB, NT, IPT, MINB, LBW>()
 
 static const OnesweepConfig cfg_v0[] = {
-  O(0, 256, 40, 3, 7),
+  OB(0, 256, 40, 3, 7),
   C(0, 256, 32, 4),
   O(0, 256, 32, 4, 7),
   O(0, 256, 36, 3, 7),
@@ -25,13 +26,13 @@ static const OnesweepConfig cfg_v2[] = {
   C(2, 256, 32, 3)
 };
 static const OnesweepConfig cfg_v4[] = {
-  O(4, 256, 36, 3, 7),
+  OB(4, 256, 36, 3, 7),
   C(4, 256, 36, 3),
   O(4, 256, 32, 3, 7),
   T(4, 256, 24, 3, 4)
 };
 static const OnesweepConfig cfg_v8[] = {
-  O(8, 256, 20, 3, 7),
+  OB(8, 256, 20, 3, 7),
   C(8, 256, 20, 3)
 };
 static const OnesweepConfig cfg_v16[] = {

@@ -45,7 +45,8 @@ enum OnesweepOpt
 {
   OPT_FMA_NOT   = 1, // per-lane ballot complement as a predicated IMAD (FMA pipe) instead of LOP3 (ALU pipe)
   OPT_LB_WINDOW = 2, // look-back polls 8 predecessors per round trip
-  OPT_CTR16     = 4  // 16-bit warp counters: half the words per bank, fewer shared-memory bank conflicts
+  OPT_CTR16     = 4, // 16-bit warp counters: half the words per bank, fewer shared-memory bank conflicts
+  OPT_BUCKET    = 8  // the digit is the key's destination bucket against PassArgs::splitters (multi-GPU partition pass)
 };
 
 template <class U, int VBYTES, int NT, int IPT, int OPT = 0>
@@ -57,7 +58,9 @@ struct OnesweepSmem
   static constexpr int CTR_BYTES   = (OPT & OPT_CTR16) ? 2 : 4;
   static constexpr uint32_t OFF_WARP = 0;                             // u32/u16 [NW][256] running offsets
   static constexpr uint32_t OFF_GOFF = OFF_WARP + NW * RADIX * CTR_BYTES; // u64 [256] per-digit output offsets
-  static constexpr uint32_t OFF_MISC = OFF_GOFF + RADIX * 8;          // u32 [16]
+  static constexpr uint32_t OFF_END  = OFF_GOFF + RADIX * 8;          // u32 [256] end of each digit's staged run
+                                                                      // (bucket mode only, else empty)
+  static constexpr uint32_t OFF_MISC = OFF_END + ((OPT & 8) ? RADIX * 4 : 0); // u32 [16]
   static constexpr uint32_t OFF_DATA = OFF_MISC + 64;                 // staged tile (16-byte aligned)
   static constexpr size_t BYTES      = size_t(OFF_DATA) + size_t(TILE) * ITEM_BYTES;
 };
@@ -223,6 +226,29 @@ __device__ __forceinline__ uint32_t pass_digit(U key, int shift, uint32_t mask, 
   return uint32_t(key >> shift) & mask;
 }
 
+// The digit of one key for this launch: bits [shift, shift + 8) of the bit-ordered key, or (bucket mode) the key's
+// destination bucket against the splitters.  Monotone in the key, so the all-ones padding key gets the largest digit.
+template <bool FLOATK, bool BUCKET, class U>
+__device__ __forceinline__ uint32_t tile_digit(const PassArgs& a, U key, int shift, uint32_t mask, U neg_zero, U pos_zero)
+{
+  if (BUCKET)
+  {
+    if (FLOATK)
+    {
+      key = key == neg_zero ? pos_zero : key;
+    }
+    uint32_t id = 0;
+#pragma unroll 1
+    for (int j = 0; j < a.num_splitters; ++j)
+    {
+      const U s = U(a.splitters[j]);
+      id += (key > s ? 1u : 0u) + (key >= s ? 1u : 0u);
+    }
+    return id;
+  }
+  return pass_digit<FLOATK>(key, shift, mask, neg_zero, pos_zero);
+}
+
 // warp counters: 32-bit, or 16-bit (OPT_CTR16: two digits per word, so a warp-wide access touches at most four
 // distinct words per bank instead of eight)
 template <bool C16>
@@ -343,6 +369,7 @@ __device__ __forceinline__ void onesweep_tile(
   using V = typename value_of<VBYTES>::type;
   constexpr int NW       = L::NW;
   constexpr bool C16     = (OPT & OPT_CTR16) != 0;
+  constexpr bool BUCKET  = (OPT & OPT_BUCKET) != 0;
   constexpr uint32_t CB  = L::CTR_BYTES;
 
   const uint32_t tid   = threadIdx.x;
@@ -395,12 +422,13 @@ __device__ __forceinline__ void onesweep_tile(
   // the value the group leader stores anyway, and it is undone for free by staging at s_data - one item.  Besides
   // halving the registers, the PRMT packing stops ptxas from keeping BOTH addends of every rank alive.
   uint32_t rank2[(IPT + 1) / 2];
+  uint32_t bid[BUCKET ? (IPT + 3) / 4 : 1];
   const uint32_t lt_mask = lanemask_lt();
   const uint32_t gt_mask = lanemask_gt();
 #pragma unroll
   for (int i = 0; i < IPT; ++i)
   {
-    const uint32_t d      = pass_digit<FLOATK>(key[i], shift, dmask, neg_zero, pos_zero);
+    const uint32_t d      = tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
     uint32_t b, c; // peers == b & c
     if (RANK == RANK_MATCH)
     {
@@ -422,6 +450,11 @@ __device__ __forceinline__ void onesweep_tile(
       ctr_st<C16>(ctr, next);
     }
     put16(rank2, i, next);
+    if (BUCKET)
+    {
+      // the bucket of a key costs a loop over the splitters: keep it (8 bits) instead of evaluating it again
+      bid[i / 4] = (i & 3) == 0 ? d : (bid[i / 4] | (d << (8 * (i & 3))));
+    }
   }
   __syncthreads();
 
@@ -477,7 +510,8 @@ __device__ __forceinline__ void onesweep_tile(
 #pragma unroll
   for (int i = 0; i < IPT; ++i)
   {
-    const uint32_t d = pass_digit<FLOATK>(key[i], shift, dmask, neg_zero, pos_zero);
+    const uint32_t d = BUCKET ? ((bid[i / 4] >> (8 * (i & 3))) & 0xffu)
+                              : tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
     const uint32_t r = get16(rank2, i) + ctr_ld<C16>(s_mine + d * CB);
     if (VBYTES > 0)
     {
@@ -541,6 +575,10 @@ __device__ __forceinline__ void onesweep_tile(
     {
       sts32(s_goff + tid * 4, uint32_t(gbase) - excl);
     }
+    if (BUCKET)
+    {
+      sts32(sbase + L::OFF_END + tid * 4, excl + total);
+    }
     if (a.bins_next != nullptr && tile_base + valid == a.num_items)
     {
       a.bins_next[tid] = gbase + total;
@@ -554,6 +592,9 @@ __device__ __forceinline__ void onesweep_tile(
   auto store_keys = [&](auto last_tag) {
     constexpr bool LAST = decltype(last_tag)::value;
     const XformT<U> xf(a.xf);
+    // bucket mode: a thread's staged positions grow with i, so its bucket only moves forward -- follow the staged run
+    // ends instead of evaluating the splitters again
+    uint32_t cur = 0, cur_end = BUCKET ? lds32(sbase + L::OFF_END) : 0u;
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
     {
@@ -562,7 +603,19 @@ __device__ __forceinline__ void onesweep_tile(
       if (FULL || pos < valid)
       {
         const U k = lds_t<U>(s_data + pos * uint32_t(sizeof(U)));
-        d         = pass_digit<FLOATK>(k, shift, dmask, neg_zero, pos_zero);
+        if (BUCKET)
+        {
+          while (pos >= cur_end)
+          {
+            ++cur;
+            cur_end = lds32(sbase + L::OFF_END + cur * 4);
+          }
+          d = cur;
+        }
+        else
+        {
+          d = tile_digit<FLOATK, BUCKET>(a, k, shift, dmask, neg_zero, pos_zero);
+        }
         const U o = LAST ? twiddle_out(k, xf) : k;
         if (BIG)
         {

@@ -29,51 +29,144 @@ struct SplitterSet
 
 constexpr int PART_THREADS = 512;
 
-template <class U>
+// Candidate keys: the first full round (round 1) appends every key that carries ANY of the prefixes to a compact
+// buffer; later rounds only scan that buffer (about n * prefixes / 256 keys for uniform data).  state[0] = number of
+// candidates, state[1] != 0 when the buffer overflowed (heavily duplicated keys) -- then later rounds scan all keys.
+//
+// VEC keys per thread and load (16-byte loads when the array is 16-byte aligned, else VEC = 1), two loads in flight.
+// Duplicate prefixes share one histogram row while counting (row of the first occurrence) and get copies at the end,
+// so a key belongs to at most one row: one compare loop, one warp-aggregated shared atomic.
+template <class U, int VEC>
 __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
-  const U* __restrict__ keys, unsigned long long n, const KeyXform kx, const SplitterSet prefixes, int hi_shift,
-  int lo_shift, unsigned long long* __restrict__ hist)
+  const U* __restrict__ keys, unsigned long long n, const KeyXform kx, const unsigned long long* __restrict__ d_prefixes,
+  int np, int hi_shift, int lo_shift, unsigned long long* __restrict__ hist, const U* __restrict__ cand_in,
+  const unsigned long long* __restrict__ cand_state_in, U* __restrict__ cand_out,
+  unsigned long long* __restrict__ cand_state_out, unsigned long long cand_capacity)
 {
   __shared__ unsigned int sh[MAX_SPLITTERS * RADIX];
-  const int np = prefixes.count;
+  __shared__ unsigned long long s_prefix[MAX_SPLITTERS + 1];
+  __shared__ int s_first[MAX_SPLITTERS + 1];
+  __shared__ unsigned int s_bitmap[8]; // round 1: which top bytes are prefixes
+  const bool one_byte_prefix = hi_shift == int(sizeof(U) * 8) - RADIX_BITS;
+  if (threadIdx.x < 8)
+  {
+    s_bitmap[threadIdx.x] = 0;
+  }
   for (int i = threadIdx.x; i < np * RADIX; i += PART_THREADS)
   {
     sh[i] = 0;
   }
   __syncthreads();
-  const XformT<U> xf(kx);
-  constexpr int UNROLL = 4; // independent loads in flight per thread
-  const unsigned long long stride = (unsigned long long) gridDim.x * PART_THREADS * UNROLL;
-  // whole blocks iterate together (the trip count only depends on blockIdx) so the ballots below are convergent
-  for (unsigned long long base = (unsigned long long) blockIdx.x * PART_THREADS * UNROLL; base < n; base += stride)
+  if (threadIdx.x < np)
   {
-    U raw[UNROLL];
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
+    const unsigned long long pf = d_prefixes[threadIdx.x];
+    int first                   = threadIdx.x;
+    for (int q = int(threadIdx.x) - 1; q >= 0; --q)
     {
-      const unsigned long long i = base + (unsigned long long) u * PART_THREADS + threadIdx.x;
-      raw[u]                     = i < n ? keys[i] : U(0);
+      first = d_prefixes[q] == pf ? q : first;
+    }
+    s_prefix[threadIdx.x] = pf;
+    s_first[threadIdx.x]  = first;
+    if (one_byte_prefix)
+    {
+      atomicOr(&s_bitmap[(pf >> 5) & 7], 1u << (pf & 31));
+    }
+  }
+  __syncthreads();
+  // source: the candidate buffer when there is one and it did not overflow (it is 16-byte aligned scratch)
+  if (cand_state_in != nullptr && cand_state_in[1] == 0)
+  {
+    keys = cand_in;
+    n    = cand_state_in[0];
+  }
+  const XformT<U> xf(kx);
+  const unsigned int lane = threadIdx.x & 31;
+  constexpr int LOADS     = 2; // independent vector loads in flight per thread
+  struct alignas(sizeof(U) * VEC) Vec
+  {
+    U k[VEC];
+  };
+  const unsigned long long per_iter = (unsigned long long) PART_THREADS * VEC * LOADS;
+  const unsigned long long stride   = (unsigned long long) gridDim.x * per_iter;
+  // whole blocks iterate together (the trip count only depends on blockIdx) so the votes below are convergent
+  for (unsigned long long base = (unsigned long long) blockIdx.x * per_iter; base < n; base += stride)
+  {
+    Vec raw[LOADS];
+#pragma unroll
+    for (int l = 0; l < LOADS; ++l)
+    {
+      const unsigned long long i = base + ((unsigned long long) l * PART_THREADS + threadIdx.x) * VEC;
+      if (i + VEC <= n)
+      {
+        raw[l] = *reinterpret_cast<const Vec*>(keys + i);
+      }
+      else
+      {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+        {
+          raw[l].k[j] = i + j < n ? keys[i + j] : U(0);
+        }
+      }
     }
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
+    for (int l = 0; l < LOADS; ++l)
     {
-      const unsigned long long i = base + (unsigned long long) u * PART_THREADS + threadIdx.x;
-      const bool in              = i < n;
-      const U v                  = digit_view(twiddle_in(raw[u], xf), xf);
-      // hi_shift == key bits on the first round: every key carries the (empty) prefix
-      const unsigned long long hi = hi_shift >= int(sizeof(U) * 8) ? 0ull : (unsigned long long) (v >> hi_shift);
-      const unsigned int bin      = (unsigned int) (v >> lo_shift) & (RADIX - 1);
-      for (int p = 0; p < np; ++p)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j)
       {
-        const bool hit        = in && hi == prefixes.v[p];
+        const unsigned long long i = base + ((unsigned long long) l * PART_THREADS + threadIdx.x) * VEC + j;
+        const U v                  = digit_view(twiddle_in(raw[l].k[j], xf), xf);
+        // hi_shift == key bits on the first round: every key carries the (empty) prefix
+        const unsigned long long hi = hi_shift >= int(sizeof(U) * 8) ? 0ull : (unsigned long long) (v >> hi_shift);
+        const unsigned int bin      = (unsigned int) (v >> lo_shift) & (RADIX - 1);
+        bool maybe                  = i < n;
+        if (one_byte_prefix)
+        {
+          maybe = maybe && ((s_bitmap[(hi >> 5) & 7] >> (hi & 31)) & 1u) != 0;
+        }
+        if (!__any_sync(0xffffffffu, maybe))
+        {
+          continue; // the usual case in a full scan: nobody in the warp carries a prefix
+        }
+        int row = -1;
+        if (maybe)
+        {
+          for (int p = 0; p < np; ++p)
+          {
+            row = (hi == s_prefix[p] && s_first[p] == p) ? p : row;
+          }
+        }
+        const bool hit        = row >= 0;
         const unsigned int hm = __ballot_sync(0xffffffffu, hit);
         if (hit)
         {
-          // warp-aggregated: one shared atomic per distinct bin, so all-equal keys do not serialise
-          const unsigned int peers = __match_any_sync(hm, bin);
-          if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0)
+          // warp-aggregated: one shared atomic per distinct (row, bin), so all-equal keys do not serialise
+          const unsigned int slot  = (unsigned int) row * RADIX + bin;
+          const unsigned int peers = __match_any_sync(hm, slot);
+          if ((peers & ((1u << lane) - 1u)) == 0)
           {
-            atomicAdd(&sh[p * RADIX + bin], (unsigned int) __popc(peers));
+            atomicAdd(&sh[slot], (unsigned int) __popc(peers));
+          }
+        }
+        if (cand_out != nullptr && hm != 0)
+        {
+          unsigned long long pos = 0;
+          if (lane == 0)
+          {
+            pos = atomicAdd(cand_state_out, (unsigned long long) __popc(hm));
+          }
+          pos = __shfl_sync(0xffffffffu, pos, 0);
+          if (pos + __popc(hm) <= cand_capacity)
+          {
+            if (hit)
+            {
+              cand_out[pos + __popc(hm & ((1u << lane) - 1u))] = raw[l].k[j];
+            }
+          }
+          else if (lane == 0)
+          {
+            cand_state_out[1] = 1; // overflow: later rounds scan every key
           }
         }
       }
@@ -82,7 +175,7 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
   __syncthreads();
   for (int i = threadIdx.x; i < np * RADIX; i += PART_THREADS)
   {
-    const unsigned int c = sh[i];
+    const unsigned int c = sh[s_first[i / RADIX] * RADIX + (i % RADIX)];
     if (c != 0)
     {
       atomicAdd(&hist[i], (unsigned long long) c);
@@ -141,17 +234,31 @@ __global__ void __launch_bounds__(PART_THREADS) bucket_ids_kernel(
 
 template <class U>
 static cudaError_t launch_select_t(
-  const void* keys, unsigned long long n, const KeyXform& xf, const SplitterSet& pf, int round, unsigned long long* hist,
-  int sms, cudaStream_t stream)
+  const void* keys, unsigned long long n, const KeyXform& xf, const unsigned long long* d_prefixes, int np, int round,
+  unsigned long long* hist, const void* cand_in, const unsigned long long* cand_state_in, void* cand_out,
+  unsigned long long* cand_state_out, unsigned long long cand_capacity, int sms, cudaStream_t stream)
 {
   const int bits     = int(sizeof(U) * 8);
   const int lo_shift = bits - RADIX_BITS * (round + 1);
   const int hi_shift = lo_shift + RADIX_BITS;
-  unsigned long long want = (n + PART_THREADS * 4 - 1) / (PART_THREADS * 4);
+  constexpr int VEC       = 16 / int(sizeof(U));
+  const bool aligned      = (reinterpret_cast<size_t>(keys) | reinterpret_cast<size_t>(cand_in)) % 16 == 0;
+  const unsigned long long per = (unsigned long long) PART_THREADS * 2 * (aligned ? VEC : 1);
+  unsigned long long want = (n + per - 1) / per;
   unsigned grid           = unsigned(sms) * 4;
   grid                    = want < grid ? unsigned(want) : grid;
-  select_histogram_kernel<U><<<grid, PART_THREADS, 0, stream>>>(
-    static_cast<const U*>(keys), n, xf, pf, hi_shift, lo_shift, hist);
+  if (aligned)
+  {
+    select_histogram_kernel<U, VEC><<<grid, PART_THREADS, 0, stream>>>(
+      static_cast<const U*>(keys), n, xf, d_prefixes, np, hi_shift, lo_shift, hist, static_cast<const U*>(cand_in),
+      cand_state_in, static_cast<U*>(cand_out), cand_state_out, cand_capacity);
+  }
+  else
+  {
+    select_histogram_kernel<U, 1><<<grid, PART_THREADS, 0, stream>>>(
+      static_cast<const U*>(keys), n, xf, d_prefixes, np, hi_shift, lo_shift, hist, static_cast<const U*>(cand_in),
+      cand_state_in, static_cast<U*>(cand_out), cand_state_out, cand_capacity);
+  }
   return cudaPeekAtLastError();
 }
 
@@ -201,16 +308,26 @@ int b200rs_select_histogram(
   int key_kind,
   int key_bytes,
   int descending,
-  const uint64_t* h_prefixes,
+  const uint64_t* d_prefixes,
   int num_prefixes,
   int round,
   uint64_t* d_hist,
+  const void* d_candidates_in,
+  const uint64_t* d_candidate_state_in,
+  void* d_candidates_out,
+  uint64_t* d_candidate_state_out,
+  uint64_t candidate_capacity,
   b200rs_stream_t stream_)
 {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if ((d_candidate_state_in != nullptr && d_candidates_in == nullptr)
+      || (d_candidates_out != nullptr && d_candidate_state_out == nullptr))
+  {
+    return int(cudaErrorInvalidValue);
+  }
   if (key_kind < 0 || key_kind > 2 || (key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8)
       || (key_kind == 2 && key_bytes < 4) || num_prefixes < 0 || num_prefixes > MAX_SPLITTERS || round < 0
-      || round >= key_bytes || d_hist == nullptr || (num_prefixes > 0 && h_prefixes == nullptr))
+      || round >= key_bytes || d_hist == nullptr || (num_prefixes > 0 && d_prefixes == nullptr))
   {
     return int(cudaErrorInvalidValue);
   }
@@ -219,6 +336,10 @@ int b200rs_select_histogram(
     return 0;
   }
   cudaError_t e = cudaMemsetAsync(d_hist, 0, size_t(num_prefixes) * RADIX * sizeof(uint64_t), stream);
+  if (e == cudaSuccess && d_candidates_out != nullptr)
+  {
+    e = cudaMemsetAsync(d_candidate_state_out, 0, 2 * sizeof(uint64_t), stream);
+  }
   if (e != cudaSuccess || num_items == 0)
   {
     return int(e);
@@ -228,20 +349,21 @@ int b200rs_select_histogram(
   {
     return rc;
   }
-  SplitterSet pf;
-  pf.count = num_prefixes;
-  for (int i = 0; i < num_prefixes; ++i)
-  {
-    pf.v[i] = h_prefixes[i];
-  }
+  const unsigned long long* pf  = reinterpret_cast<const unsigned long long*>(d_prefixes);
+  const unsigned long long* csi = reinterpret_cast<const unsigned long long*>(d_candidate_state_in);
+  unsigned long long* cso       = reinterpret_cast<unsigned long long*>(d_candidate_state_out);
   const KeyXform xf         = make_xform(key_kind, key_bytes, descending);
   unsigned long long* hist = reinterpret_cast<unsigned long long*>(d_hist);
   switch (key_bytes)
   {
-    case 1: return int(launch_select_t<uint8_t>(d_keys, num_items, xf, pf, round, hist, sms, stream));
-    case 2: return int(launch_select_t<uint16_t>(d_keys, num_items, xf, pf, round, hist, sms, stream));
-    case 4: return int(launch_select_t<uint32_t>(d_keys, num_items, xf, pf, round, hist, sms, stream));
-    default: return int(launch_select_t<uint64_t>(d_keys, num_items, xf, pf, round, hist, sms, stream));
+    case 1: return int(launch_select_t<uint8_t>(d_keys, num_items, xf, pf, num_prefixes, round, hist, d_candidates_in, csi,
+                                                 d_candidates_out, cso, candidate_capacity, sms, stream));
+    case 2: return int(launch_select_t<uint16_t>(d_keys, num_items, xf, pf, num_prefixes, round, hist, d_candidates_in, csi,
+                                                 d_candidates_out, cso, candidate_capacity, sms, stream));
+    case 4: return int(launch_select_t<uint32_t>(d_keys, num_items, xf, pf, num_prefixes, round, hist, d_candidates_in, csi,
+                                                 d_candidates_out, cso, candidate_capacity, sms, stream));
+    default: return int(launch_select_t<uint64_t>(d_keys, num_items, xf, pf, num_prefixes, round, hist, d_candidates_in, csi,
+                                                 d_candidates_out, cso, candidate_capacity, sms, stream));
   }
 }
 

@@ -72,23 +72,37 @@ class CudaOps:
 
     def __init__(self):
         self.lib = _native.lib()  # raises if the CUDA library is absent: there is no CPU path
+        self._scratch = {}
 
-    def sort_pairs(self, keys, values, descending, preserve_input=False):
+    def scratch(self, name, numel, dtype, device):
+        """Grow-only scratch tensor kept across calls (stream-ordered reuse: one stream per CudaOps object).  Scratch
+        never leaves this module; results handed to the caller are always fresh or caller-provided tensors."""
         import torch
 
-        from .radix_sort import DoubleBuffer, SortOrder, radix_sort
+        t = self._scratch.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype or t.device != device:
+            t = torch.empty(max(int(numel), 1), dtype=dtype, device=device)
+            self._scratch[name] = t
+        return t[:numel]
+
+    def sort_pairs(self, keys, values, descending, preserve_input=False, out=None):
+        import torch
+
+        from .radix_sort import DoubleBuffer, SortOrder, make_radix_sort, radix_sort
 
         n = keys.numel()
         if n == 0:
             return keys, values
         order = SortOrder.DESCENDING if descending else SortOrder.ASCENDING
         if preserve_input:
-            # pointer API: the caller's shard is left untouched (device_radix_sort.cuh:315)
-            okeys = torch.empty_like(keys)
-            ovals = torch.empty_like(values) if values is not None else None
-            keep = radix_sort(d_in_keys=keys, d_out_keys=okeys, d_in_values=values, d_out_values=ovals, num_items=n,
-                              order=order)
-            del keep
+            # pointer API: the caller's shard is left untouched (device_radix_sort.cuh:315); temp storage is scratch
+            okeys = out[0] if out is not None else torch.empty_like(keys)
+            ovals = (out[1] if out is not None else torch.empty_like(values)) if values is not None else None
+            sorter = make_radix_sort(d_in_keys=keys, d_out_keys=okeys, d_in_values=values, d_out_values=ovals,
+                                     order=order)
+            kw = dict(d_in_keys=keys, d_out_keys=okeys, d_in_values=values, d_out_values=ovals, num_items=n)
+            nbytes = sorter(temp_storage=None, **kw)
+            sorter(temp_storage=self.scratch("sort_temp", nbytes, torch.uint8, keys.device), **kw)
             return okeys, ovals
         kb = DoubleBuffer(keys, torch.empty_like(keys))
         vb = DoubleBuffer(values, torch.empty_like(values)) if values is not None else None
@@ -127,20 +141,30 @@ class CudaOps:
         _native.check(rc, "b200rs_digit_histogram")
         return out.view(1, RADIX)
 
-    def select_histogram(self, keys, prefixes: np.ndarray, rnd: int, descending):
-        """(len(prefixes), 256) int64: per candidate prefix, histogram of digit `rnd` (MSD first) of the keys whose
-        higher digits equal the prefix."""
-        import ctypes
-
+    def select_histogram(self, keys, prefixes, rnd: int, descending, candidates="none"):
+        """(len(prefixes), 256) int64: per candidate prefix (int64 device tensor holding the bit pattern of the high
+        digits chosen so far), histogram of digit `rnd` (MSD first) of the keys whose higher digits equal the prefix.
+        candidates: "emit" also compacts the keys that carry any prefix into a scratch buffer, "use" scans that buffer
+        (written by the previous "emit" over the same keys) instead of all keys, "none" does neither."""
         import torch
 
         kdt = _torch_np_dtype(keys)
-        m = int(prefixes.size)
+        m = int(prefixes.numel())
+        n = keys.numel()
         out = torch.empty((m, RADIX), dtype=torch.int64, device=keys.device)
-        arr = (ctypes.c_uint64 * max(m, 1))(*[int(x) for x in prefixes])
+        cap = n // 8 + (1 << 16)
+        cin = cst_in = cout = cst_out = 0
+        if candidates != "none" and n:
+            cand = self.scratch("select_cand", cap, keys.dtype, keys.device)
+            state = self.scratch("select_state", 2, torch.int64, keys.device)
+            if candidates == "emit":
+                cout, cst_out = cand.data_ptr(), state.data_ptr()
+            else:
+                cin, cst_in = cand.data_ptr(), state.data_ptr()
         rc = self.lib.b200rs_select_histogram(
-            keys.data_ptr() if keys.numel() else 0, keys.numel(), key_kind_of(kdt), kdt.itemsize,
-            int(bool(descending)), arr, m, rnd, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            keys.data_ptr() if n else 0, n, key_kind_of(kdt), kdt.itemsize, int(bool(descending)),
+            prefixes.data_ptr(), m, rnd, out.data_ptr(), cin or None, cst_in or None, cout or None, cst_out or None,
+            cap, torch.cuda.current_stream().cuda_stream)
         _native.check(rc, "b200rs_select_histogram")
         return out
 
@@ -160,6 +184,39 @@ class CudaOps:
             torch.cuda.current_stream().cuda_stream)
         _native.check(rc, "b200rs_bucket_ids")
         return ids
+
+    def partition_by_splitters(self, keys, values, splitters: np.ndarray, sizes: np.ndarray, descending):
+        """Stable partition of (keys, values) into destination-bucket order in ONE onesweep launch whose digit is the
+        bucket of the key (b200rs_partition_by_splitters).  Returns None when the library has no such kernel for these
+        key / value widths."""
+        import ctypes
+
+        import torch
+
+        n = keys.numel()
+        kdt = _torch_np_dtype(keys)
+        vb = values.element_size() if values is not None else 0
+        m = int(splitters.size)
+        sp = (ctypes.c_uint64 * max(m, 1))(*[int(x) for x in splitters])
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+        bo = (ctypes.c_uint64 * len(offs))(*[int(x) for x in offs])
+        stream = torch.cuda.current_stream().cuda_stream
+        nbytes = ctypes.c_size_t(0)
+        args = (n, key_kind_of(kdt), kdt.itemsize, vb, int(bool(descending)), sp, m, bo, stream)
+        rc = self.lib.b200rs_partition_by_splitters(None, ctypes.byref(nbytes), None, None, None, None, *args)
+        if rc == 801:  # cudaErrorNotSupported
+            return None
+        _native.check(rc, "b200rs_partition_by_splitters (size query)")
+        pk = self.scratch("part_keys", n, keys.dtype, keys.device)
+        pv = self.scratch("part_vals", n, values.dtype, values.device) if values is not None else None
+        if n == 0:
+            return pk, pv
+        temp = self.scratch("part_temp", nbytes.value, torch.uint8, keys.device)
+        rc = self.lib.b200rs_partition_by_splitters(
+            temp.data_ptr(), ctypes.byref(nbytes), keys.data_ptr(), pk.data_ptr(),
+            values.data_ptr() if values is not None else None, pv.data_ptr() if pv is not None else None, *args)
+        _native.check(rc, "b200rs_partition_by_splitters")
+        return pk, pv
 
     def partition(self, ids, nbits, keys, values):
         """Stable partition of (keys, values) by the bucket id of each item: one radix pass over the low `nbits` bits
@@ -189,51 +246,69 @@ class CudaOps:
 # ----------------------------------------------------------------------------------------------- splitter selection
 def select_splitters_unsorted(keys, targets, *, kind, key_bytes, descending, ops, group, dist, stats=None):
     """Exact splitters from the UNSORTED shard.  For every global target rank t finds the bit-ordered value x of the
-    t-th smallest key of the whole job by MSD radix select, and returns (bounds, splitters): bounds[(world, nt)] =
-    number of items of each source rank that go to ranks <= the target's, counted in the order "bucket id, then local
-    position"; splitters = the distinct x values, ascending (uint64)."""
+    t-th smallest key of the whole job by MSD radix select, and returns (bounds, splitters, sizes): bounds[(world, nt)]
+    = number of items of each source rank that go to ranks <= the target's, counted in the order "bucket id, then local
+    position"; splitters = the distinct x values, ascending (uint64); sizes = this rank's bucket sizes in bucket-id
+    order.  The rounds keep their state on the device (the bin pick is a handful of tiny tensor ops), so the host only
+    waits once, at the end."""
     import torch
 
     world = dist.get_world_size(group)
     nt = len(targets)
     if nt == 0:
-        return np.zeros((world, 0), dtype=np.int64), np.zeros(0, dtype=np.uint64)
-    tgt = np.maximum(np.asarray(targets, dtype=np.int64), 1)
-    prefix = np.zeros(nt, dtype=np.uint64)
-    below = np.zeros(nt, dtype=np.int64)     # global count of keys whose high digits are below the prefix
-    lt_local = np.zeros(nt, dtype=np.int64)  # the same, for this rank's shard only
-    eq_local = np.zeros(nt, dtype=np.int64)
+        return np.zeros((world, 0), dtype=np.int64), np.zeros(0, dtype=np.uint64), np.array([keys.numel()])
+    dev = keys.device
+    tgt = torch.from_numpy(np.maximum(np.asarray(targets, dtype=np.int64), 1)).to(dev)
+    prefix = torch.zeros(nt, dtype=torch.int64, device=dev)    # bit pattern of the digits chosen so far
+    below = torch.zeros(nt, dtype=torch.int64, device=dev)     # global count of keys whose high digits are below it
+    lt_local = torch.zeros(nt, dtype=torch.int64, device=dev)  # the same, for this rank's shard only
+    eq_local = torch.zeros(nt, dtype=torch.int64, device=dev)
     for rnd in range(key_bytes):
-        uniq, inv = np.unique(prefix, return_inverse=True)
         if rnd == 0:
-            h_local = ops.top_digit_histogram(keys, descending)
+            h_local = ops.top_digit_histogram(keys, descending).expand(nt, RADIX)
         else:
-            h_local = ops.select_histogram(keys, uniq, rnd, descending)
-        h_glob = h_local.clone()
+            # the first full scan compacts the keys that can still matter; later rounds only look at those
+            mode = "none" if key_bytes <= 2 else ("emit" if rnd == 1 else "use")
+            h_local = ops.select_histogram(keys, prefix, rnd, descending, candidates=mode)
+        h_glob = h_local.contiguous().clone()
         _all_reduce(dist, h_glob, group)
-        both = torch.stack([h_local, h_glob]).cpu().numpy()  # (2, len(uniq), 256)
-        for i in range(nt):
-            hl, hg = both[0, inv[i]], both[1, inv[i]]
-            cum = np.cumsum(hg)
-            b = min(int(np.searchsorted(cum, tgt[i] - below[i], side="left")), RADIX - 1)
-            if b > 0:
-                below[i] += int(cum[b - 1])
-                lt_local[i] += int(hl[:b].sum())
-            eq_local[i] = int(hl[b])
-            prefix[i] = (prefix[i] << np.uint64(RADIX_BITS)) + np.uint64(b)
-    mine = torch.from_numpy(np.stack([lt_local, eq_local])).to(keys.device)
+        cum_g = torch.cumsum(h_glob, dim=1)
+        cum_l = torch.cumsum(h_local, dim=1)
+        # first bin whose global running count reaches the (remaining) target rank
+        b = torch.searchsorted(cum_g, (tgt - below).unsqueeze(1)).squeeze(1).clamp_(max=RADIX - 1)
+        prev = (b - 1).clamp_(min=0).unsqueeze(1)
+        has_prev = b > 0
+        below = below + torch.where(has_prev, cum_g.gather(1, prev).squeeze(1), torch.zeros_like(below))
+        lt_local = lt_local + torch.where(has_prev, cum_l.gather(1, prev).squeeze(1), torch.zeros_like(below))
+        eq_local = h_local.gather(1, b.unsqueeze(1)).squeeze(1)
+        prefix = prefix * RADIX + b  # wraps like the unsigned 64-bit value it stands for
+    mine = torch.stack([lt_local, eq_local, prefix]).contiguous()
     allc = [torch.empty_like(mine) for _ in range(world)]
     _all_gather(dist, allc, mine, group)
-    allc = torch.stack(allc).cpu().numpy()  # (world, 2, nt)
+    allc = torch.stack(allc).cpu().numpy()  # (world, 3, nt): the only host wait of the selection
     lt_all, eq_all = allc[:, 0, :], allc[:, 1, :]
+    rank = dist.get_rank(group)
+    lt_mine, eq_mine = lt_all[rank], eq_all[rank]
+    prefix_np = allc[rank, 2, :].view(np.uint64) & np.uint64((1 << (8 * key_bytes)) - 1 if key_bytes < 8 else 2**64 - 1)
     need = np.asarray(targets, dtype=np.int64) - lt_all.sum(axis=0)  # items EQUAL to the splitter that go to lower ranks
     before = np.cumsum(eq_all, axis=0) - eq_all
     take = np.clip(need[None, :] - before, 0, eq_all)
     if stats is not None:
         stats["splitter_rounds"] = key_bytes
-        stats["splitters_bit_ordered"] = [int(x) for x in prefix]
+        stats["splitters_bit_ordered"] = [int(x) for x in prefix_np]
     assert (take.sum(axis=0) == np.clip(need, 0, None)).all(), "splitter selection is inconsistent"
-    return lt_all + take, np.unique(prefix)
+    splitters, first = np.unique(prefix_np, return_index=True)
+    # local bucket sizes in bucket-id order: (below u0), (== u0), (between u0 and u1), (== u1), ..., (above the last)
+    lt_u, eq_u = lt_mine[first], eq_mine[first]
+    sizes = np.zeros(2 * len(splitters) + 1, dtype=np.int64)
+    prev_end = 0
+    for i in range(len(splitters)):
+        sizes[2 * i] = lt_u[i] - prev_end
+        sizes[2 * i + 1] = eq_u[i]
+        prev_end = lt_u[i] + eq_u[i]
+    sizes[-1] = keys.numel() - prev_end
+    assert sizes.min() >= 0, "bucket sizes are inconsistent"
+    return lt_all + take, splitters, sizes
 
 
 def select_splitters(sorted_keys, targets, *, kind, key_bytes, descending, ops, group, dist, stats=None):
@@ -380,19 +455,30 @@ def _byte_view():
     return torch.uint8
 
 
+_DEFAULT_OPS = None
+
+
+def _default_ops():
+    global _DEFAULT_OPS
+    if _DEFAULT_OPS is None:
+        _DEFAULT_OPS = CudaOps()
+    return _DEFAULT_OPS
+
+
 def distributed_sort(keys, values=None, *, descending=False, group=None, ops=None, stats=None, protocol="partition",
-                     exchange="auto"):
+                     exchange="auto", out=None):
     """Stable distributed sort of one shard per rank; returns (keys_out, values_out) with len == len(keys).
     The caller's shard is left untouched.  ``stats`` (a dict) receives splitters, exchange counts and, on CUDA, the
     device time of each phase.  ``protocol``: "partition" (histogram select -> one partition pass -> exchange -> one
     sort) or "sort" (sort -> binary-search select -> exchange -> sort).  ``exchange``: "peer" (NVLink peer copies through
-    symmetric memory), "collective" (all-to-all-v) or "auto" (peer on CUDA + NCCL, else collective)."""
+    symmetric memory), "collective" (all-to-all-v) or "auto" (peer on CUDA + NCCL, else collective).  ``out``: optional
+    (keys_out, values_out) tensors for the result (same length and dtype as the inputs)."""
     import torch
     import torch.distributed as dist
 
     if protocol not in ("partition", "sort"):
         raise ValueError(f"unknown protocol {protocol!r}")
-    ops = ops or CudaOps()
+    ops = ops or _default_ops()
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     kdt = _torch_np_dtype(keys)
@@ -402,11 +488,11 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
     ph.mark("start")
 
     if world == 1:
-        out = ops.sort_pairs(keys, values, descending, preserve_input=True)
+        res = ops.sort_pairs(keys, values, descending, preserve_input=True, out=out)
         ph.mark("local_sort")
         if stats is not None:
             stats["phase_ms"] = ph.result()
-        return out
+        return res
 
     # rank r must end with the global stable positions [sum(n[:r]), sum(n[:r+1]))
     counts = torch.tensor([n_local], dtype=torch.int64, device=keys.device)
@@ -426,12 +512,19 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
         # 1. splitters by radix select over the unsorted shard; 2. one stable partition pass by destination bucket
         if world - 1 > 15:
             raise ValueError("the partition protocol supports up to 16 ranks (one box)")
-        bounds, splitters = select_splitters_unsorted(keys, targets, kind=kind, key_bytes=key_bytes,
-                                                      descending=descending, ops=ops, group=group, dist=dist,
-                                                      stats=stats)
+        bounds, splitters, sizes = select_splitters_unsorted(keys, targets, kind=kind, key_bytes=key_bytes,
+                                                             descending=descending, ops=ops, group=group, dist=dist,
+                                                             stats=stats)
         ph.mark("splitters")
-        ids = ops.bucket_ids(keys, splitters, descending)
-        skeys, svals = ops.partition(ids, int(2 * len(splitters)).bit_length(), keys, values)
+        fused = getattr(ops, "partition_by_splitters", None)
+        part = fused(keys, values, splitters, sizes, descending) if fused is not None else None
+        if part is None:
+            # key / value widths the fused pass is not compiled for: bucket ids + one radix pass over the ids
+            ids = ops.bucket_ids(keys, splitters, descending)
+            part = ops.partition(ids, int(2 * len(splitters)).bit_length(), keys, values)
+        skeys, svals = part
+        if stats is not None:
+            stats["partition_pass"] = "ids" if "ids" in locals() else "fused"
         ph.mark("partition")
     # boundary matrix with the implicit 0 and n columns: items [edges[i, r], edges[i, r+1]) of source i go to rank r
     edges = np.concatenate([np.zeros((world, 1), dtype=np.int64), bounds, n_all[:, None]], axis=1)
@@ -461,7 +554,10 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
     ph.mark("exchange")
 
     # 4. final local stable sort (peer mode: the receive buffers are shared scratch, so the result goes elsewhere)
-    out = ops.sort_pairs(rkeys, rvals, descending, preserve_input=peer_done)
+    if peer_done or out is not None:
+        res = ops.sort_pairs(rkeys, rvals, descending, preserve_input=True, out=out)
+    else:
+        res = ops.sort_pairs(rkeys, rvals, descending)
     ph.mark("final_sort")
     if stats is not None:
         stats["protocol"] = protocol
@@ -472,7 +568,7 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
         stats["exchange_bytes_out"] = (n_local - send[rank]) * item
         stats["exchange_bytes_in"] = (n_local - recv[rank]) * item
         stats["phase_ms"] = ph.result()
-    return out
+    return res
 
 
 _A2A_VIEW = {1: "uint8", 2: "int16", 4: "int32", 8: "int64"}

@@ -167,9 +167,13 @@ B200RS_API int b200rs_splitter_ranks(
  * Both work on an UNSORTED shard, in the sort's own key domain (bit-ordered value after the key transform, descending
  * included, -0.0 viewed as +0.0), i.e. "equal" means what b200rs_sort treats as equal.
  *
- * b200rs_select_histogram: one round of the exact MSD radix select.  h_prefixes (HOST array, num_prefixes <= 15) holds
- * the high digits chosen so far, as values of `round` digits (round 0: all zero).  d_hist[p * 256 + b] receives the
- * number of local keys whose top `round` digits equal h_prefixes[p] and whose next 8-bit digit is b.  Overwritten.
+ * b200rs_select_histogram: one round of the exact MSD radix select.  d_prefixes (DEVICE array, num_prefixes <= 15, so a
+ * round can consume the previous round's choice without a host round trip) holds the high digits chosen so far, as
+ * values of `round` digits (round 0: all zero); duplicates are allowed.  Optional candidate compaction: with
+ * d_candidates_out / d_candidate_state_out (uint64[2] = {count, overflow flag}) every key that carries one of the
+ * prefixes is also appended to d_candidates_out (capacity in keys; on overflow the flag is set); with d_candidates_in /
+ * d_candidate_state_in a later round scans that buffer instead of all keys (or all keys if the flag is set).  d_hist[p * 256 + b] receives the
+ * number of local keys whose top `round` digits equal d_prefixes[p] and whose next 8-bit digit is b.  Overwritten.
  *
  * b200rs_bucket_ids: h_splitters (HOST array, strictly increasing bit-ordered values, num_splitters <= 15);
  * d_ids[i] = 2 * #{j : splitter_j < key_i} + [key_i == some splitter_j]  (uint8).
@@ -184,10 +188,15 @@ B200RS_API int b200rs_select_histogram(
   int key_kind,
   int key_bytes,
   int descending,
-  const uint64_t* h_prefixes,
+  const uint64_t* d_prefixes,
   int num_prefixes,
   int round,
   uint64_t* d_hist,
+  const void* d_candidates_in,
+  const uint64_t* d_candidate_state_in,
+  void* d_candidates_out,
+  uint64_t* d_candidate_state_out,
+  uint64_t candidate_capacity,
   b200rs_stream_t stream);
 
 B200RS_API int b200rs_bucket_ids(
@@ -199,6 +208,33 @@ B200RS_API int b200rs_bucket_ids(
   const uint64_t* h_splitters,
   int num_splitters,
   uint8_t* d_ids,
+  b200rs_stream_t stream);
+
+/*
+ * The partition pass of the multi-GPU protocol as ONE onesweep launch: keys (and values) are moved, stably, into
+ * destination-bucket order, the bucket of a key being 2 * #{splitters below it} + [it equals a splitter] -- what
+ * b200rs_bucket_ids computes, here evaluated inside the kernel so no id array is written or read.
+ * h_splitters: HOST array, strictly increasing bit-ordered values (num_splitters <= 15).  h_bucket_offsets: HOST array
+ * of 2 * num_splitters + 1 exclusive output offsets (the caller knows the bucket sizes from the select rounds).
+ * Two-phase temp-storage query like b200rs_sort.  Compiled for 4- and 8-byte keys with 0-, 4- or 8-byte values and
+ * fewer than 2^30 items; anything else returns cudaErrorNotSupported (callers fall back to b200rs_bucket_ids +
+ * b200rs_sort on the ids).  Input arrays are not modified.
+ */
+B200RS_API int b200rs_partition_by_splitters(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int descending,
+  const uint64_t* h_splitters,
+  int num_splitters,
+  const uint64_t* h_bucket_offsets,
   b200rs_stream_t stream);
 
 /* Number of kernel launches / async ops the last b200rs_sort call on this host thread enqueued

@@ -65,9 +65,10 @@ class OracleOps:
         return _view(k.view(np.dtype(f"u{kb}")), okind(k.dtype), kb, descending), kb
 
     def top_digit_histogram(self, keys, descending):
-        return self.select_histogram(keys, np.zeros(1, dtype=np.uint64), 0, descending)
+        return self.select_histogram(keys, torch.zeros(1, dtype=torch.int64), 0, descending)
 
-    def select_histogram(self, keys, prefixes, rnd, descending):
+    def select_histogram(self, keys, prefixes, rnd, descending, candidates="none"):
+        prefixes = prefixes.cpu().numpy().astype(np.int64).view(np.uint64)
         v, kb = self._kv(keys, descending)
         lo = np.uint64(8 * kb - 8 * (rnd + 1))
         hi = (v >> (lo + np.uint64(8))) if int(lo) + 8 < 64 else np.zeros_like(v)
@@ -92,7 +93,7 @@ class OracleOps:
         pv = to_torch(to_np(values)[order]) if values is not None else None
         return pk, pv
 
-    def sort_pairs(self, keys, values, descending, preserve_input=False):
+    def sort_pairs(self, keys, values, descending, preserve_input=False, out=None):
         k = to_np(keys)
         if values is None:
             return to_torch(oracle_sort(k, descending=descending)), None

@@ -40,8 +40,21 @@ def test_select_histogram_and_bucket_ids(dtype, dist):
                 shift = np.uint64(8 * kb - 8 * rnd)
                 have = np.unique(v >> shift)[:6] if n else np.zeros(0, dtype=np.uint64)
                 prefixes = np.unique(np.concatenate([have, np.array([1], dtype=np.uint64)]))
-                got = cuda.select_histogram(dk, prefixes, rnd, desc).cpu()
-                assert torch.equal(got, ref.select_histogram(hk, prefixes, rnd, desc)), (n, desc, rnd)
+                tp = torch.from_numpy(prefixes.view(np.int64).copy())
+                got = cuda.select_histogram(dk, tp.cuda(), rnd, desc).cpu()
+                assert torch.equal(got, ref.select_histogram(hk, tp, rnd, desc)), (n, desc, rnd)
+            if kb >= 4 and n:
+                # candidate compaction: round 1 emits the keys that carry a 1-byte prefix, round 2 scans only those
+                # (all-equal keys overflow the candidate buffer, which must fall back to scanning every key)
+                p2 = np.unique(v >> np.uint64(8 * kb - 16))[:5]
+                p2 = np.unique(np.concatenate([p2, np.array([3], dtype=np.uint64)]))
+                p1 = np.unique(p2 >> np.uint64(8))
+                t1 = torch.from_numpy(p1.view(np.int64).copy())
+                t2 = torch.from_numpy(p2.view(np.int64).copy())
+                got1 = cuda.select_histogram(dk, t1.cuda(), 1, desc, candidates="emit").cpu()
+                assert torch.equal(got1, ref.select_histogram(hk, t1, 1, desc)), (n, desc, "emit round")
+                got2 = cuda.select_histogram(dk, t2.cuda(), 2, desc, candidates="use").cpu()
+                assert torch.equal(got2, ref.select_histogram(hk, t2, 2, desc)), (n, desc, "candidate round")
             vs = np.sort(v)
             picks = vs[[n // 10, n // 2, n // 2, (9 * n) // 10]] if n else np.zeros(0, dtype=np.uint64)
             qs = np.unique(np.concatenate([picks, np.array([0, 5], dtype=np.uint64)]))
@@ -54,3 +67,14 @@ def test_select_histogram_and_bucket_ids(dtype, dist):
                                        torch.arange(n, dtype=torch.int32))
                 assert torch.equal(pk.cpu().view(torch.uint8), rk.view(torch.uint8)), (n, desc, "partition keys")
                 assert torch.equal(pv.cpu(), rv), (n, desc, "partition values")
+                # the fused pass (one onesweep launch whose digit is the bucket) must give the same arrangement
+                sizes = np.bincount(ref.bucket_ids(hk, qs, desc).numpy(), minlength=2 * len(qs) + 1)
+                for vals in (torch.arange(n, dtype=torch.int32, device="cuda"), None):
+                    fused = cuda.partition_by_splitters(dk, vals, qs, sizes, desc)
+                    if fused is None:
+                        assert kb < 4, "the fused partition pass must exist for 4- and 8-byte keys"
+                        continue
+                    assert torch.equal(fused[0].cpu().view(torch.uint8), rk.view(torch.uint8)), (n, desc, "fused keys")
+                    if vals is not None:
+                        assert torch.equal(fused[1].cpu(), rv), (n, desc, "fused values")
+                    assert torch.equal(dk.cpu().view(torch.uint8), hk.view(torch.uint8)), "input modified"
