@@ -28,10 +28,14 @@ struct SplitterSet
 };
 
 constexpr int PART_THREADS = 512;
+constexpr int SELECT_STATE_WORDS = 2 + 1024; // candidate state: {unused, overflow flag, per-CTA counts}
 
 // Candidate keys: the first full round (round 1) appends every key that carries ANY of the prefixes to a compact
-// buffer; later rounds only scan that buffer (about n * prefixes / 256 keys for uniform data).  state[0] = number of
-// candidates, state[1] != 0 when the buffer overflowed (heavily duplicated keys) -- then later rounds scan all keys.
+// buffer; later rounds only scan that buffer (about n * prefixes / 256 keys for uniform data).  Every CTA owns one
+// slice of the buffer (capacity / gridDim.x keys) and reserves space with a shared-memory counter, so there is no
+// global atomic on the way; state[1] != 0 when some slice overflowed (heavily duplicated keys) -- then later rounds
+// scan all keys -- and state[2 + b] = number of candidates in the slice of CTA b.  Emitting and consuming launches use
+// the same grid (SELECT_STATE_WORDS bounds it).
 //
 // VEC keys per thread and load (16-byte loads when the array is 16-byte aligned, else VEC = 1), two loads in flight.
 // Duplicate prefixes share one histogram row while counting (row of the first occurrence) and get copies at the end,
@@ -47,6 +51,12 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
   __shared__ unsigned long long s_prefix[MAX_SPLITTERS + 1];
   __shared__ int s_first[MAX_SPLITTERS + 1];
   __shared__ unsigned int s_bitmap[8]; // round 1: which top bytes are prefixes
+  __shared__ unsigned int s_emitted;
+  const unsigned long long slice_cap = (cand_capacity / gridDim.x) & ~15ull; // slices stay 16-byte aligned
+  if (threadIdx.x == 0)
+  {
+    s_emitted = 0;
+  }
   const bool one_byte_prefix = hi_shift == int(sizeof(U) * 8) - RADIX_BITS;
   if (threadIdx.x < 8)
   {
@@ -73,12 +83,14 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
     }
   }
   __syncthreads();
-  // source: the candidate buffer when there is one and it did not overflow (it is 16-byte aligned scratch)
-  if (cand_state_in != nullptr && cand_state_in[1] == 0)
+  // source: this CTA's slice of the candidate buffer when there is one and no slice overflowed
+  const bool from_slice = cand_state_in != nullptr && cand_state_in[1] == 0;
+  if (from_slice)
   {
-    keys = cand_in;
-    n    = cand_state_in[0];
+    keys = cand_in + (unsigned long long) blockIdx.x * slice_cap;
+    n    = cand_state_in[2 + blockIdx.x];
   }
+  U* my_out = cand_out != nullptr ? cand_out + (unsigned long long) blockIdx.x * slice_cap : nullptr;
   const XformT<U> xf(kx);
   const unsigned int lane = threadIdx.x & 31;
   constexpr int LOADS     = 2; // independent vector loads in flight per thread
@@ -87,9 +99,10 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
     U k[VEC];
   };
   const unsigned long long per_iter = (unsigned long long) PART_THREADS * VEC * LOADS;
-  const unsigned long long stride   = (unsigned long long) gridDim.x * per_iter;
+  const unsigned long long stride   = from_slice ? per_iter : (unsigned long long) gridDim.x * per_iter;
+  const unsigned long long start    = from_slice ? 0ull : (unsigned long long) blockIdx.x * per_iter;
   // whole blocks iterate together (the trip count only depends on blockIdx) so the votes below are convergent
-  for (unsigned long long base = (unsigned long long) blockIdx.x * per_iter; base < n; base += stride)
+  for (unsigned long long base = start; base < n; base += stride)
   {
     Vec raw[LOADS];
 #pragma unroll
@@ -149,19 +162,19 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
             atomicAdd(&sh[slot], (unsigned int) __popc(peers));
           }
         }
-        if (cand_out != nullptr && hm != 0)
+        if (my_out != nullptr && hm != 0)
         {
-          unsigned long long pos = 0;
+          unsigned int pos = 0;
           if (lane == 0)
           {
-            pos = atomicAdd(cand_state_out, (unsigned long long) __popc(hm));
+            pos = atomicAdd(&s_emitted, (unsigned int) __popc(hm));
           }
           pos = __shfl_sync(0xffffffffu, pos, 0);
-          if (pos + __popc(hm) <= cand_capacity)
+          if ((unsigned long long) pos + __popc(hm) <= slice_cap)
           {
             if (hit)
             {
-              cand_out[pos + __popc(hm & ((1u << lane) - 1u))] = raw[l].k[j];
+              my_out[pos + __popc(hm & ((1u << lane) - 1u))] = raw[l].k[j];
             }
           }
           else if (lane == 0)
@@ -173,6 +186,10 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
     }
   }
   __syncthreads();
+  if (my_out != nullptr && threadIdx.x == 0)
+  {
+    cand_state_out[2 + blockIdx.x] = s_emitted; // (beyond slice_cap only together with the overflow flag)
+  }
   for (int i = threadIdx.x; i < np * RADIX; i += PART_THREADS)
   {
     const unsigned int c = sh[s_first[i / RADIX] * RADIX + (i % RADIX)];
@@ -246,6 +263,7 @@ static cudaError_t launch_select_t(
   const unsigned long long per = (unsigned long long) PART_THREADS * 2 * (aligned ? VEC : 1);
   unsigned long long want = (n + per - 1) / per;
   unsigned grid           = unsigned(sms) * 4;
+  grid                    = grid > unsigned(SELECT_STATE_WORDS - 2) ? unsigned(SELECT_STATE_WORDS - 2) : grid;
   grid                    = want < grid ? unsigned(want) : grid;
   if (aligned)
   {
@@ -338,7 +356,7 @@ int b200rs_select_histogram(
   cudaError_t e = cudaMemsetAsync(d_hist, 0, size_t(num_prefixes) * RADIX * sizeof(uint64_t), stream);
   if (e == cudaSuccess && d_candidates_out != nullptr)
   {
-    e = cudaMemsetAsync(d_candidate_state_out, 0, 2 * sizeof(uint64_t), stream);
+    e = cudaMemsetAsync(d_candidate_state_out, 0, SELECT_STATE_WORDS * sizeof(uint64_t), stream);
   }
   if (e != cudaSuccess || num_items == 0)
   {

@@ -156,7 +156,7 @@ class CudaOps:
         cin = cst_in = cout = cst_out = 0
         if candidates != "none" and n:
             cand = self.scratch("select_cand", cap, keys.dtype, keys.device)
-            state = self.scratch("select_state", 2, torch.int64, keys.device)
+            state = self.scratch("select_state", 2 + 1024, torch.int64, keys.device)
             if candidates == "emit":
                 cout, cst_out = cand.data_ptr(), state.data_ptr()
             else:
@@ -498,7 +498,7 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
     counts = torch.tensor([n_local], dtype=torch.int64, device=keys.device)
     allcounts = [torch.empty_like(counts) for _ in range(world)]
     _all_gather(dist, allcounts, counts, group)
-    n_all = np.array([int(c.item()) for c in allcounts], dtype=np.int64)
+    n_all = torch.cat(allcounts).cpu().numpy().astype(np.int64)  # one host wait
     targets = np.cumsum(n_all)[:-1]
 
     if protocol == "sort":

@@ -170,7 +170,7 @@ B200RS_API int b200rs_splitter_ranks(
  * b200rs_select_histogram: one round of the exact MSD radix select.  d_prefixes (DEVICE array, num_prefixes <= 15, so a
  * round can consume the previous round's choice without a host round trip) holds the high digits chosen so far, as
  * values of `round` digits (round 0: all zero); duplicates are allowed.  Optional candidate compaction: with
- * d_candidates_out / d_candidate_state_out (uint64[2] = {count, overflow flag}) every key that carries one of the
+ * d_candidates_out / d_candidate_state_out (uint64[1026]: overflow flag and per-CTA counts) every key that carries one of the
  * prefixes is also appended to d_candidates_out (capacity in keys; on overflow the flag is set); with d_candidates_in /
  * d_candidate_state_in a later round scans that buffer instead of all keys (or all keys if the flag is set).  d_hist[p * 256 + b] receives the
  * number of local keys whose top `round` digits equal d_prefixes[p] and whose next 8-bit digit is b.  Overwritten.
