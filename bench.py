@@ -41,6 +41,11 @@ WORKLOADS = {
     "sortkeys_i64_desc_2^28_bits16_48": ("int64", None, 28, "uniform", True, 16, 48),
     "sortkeys_i64_desc_2^28": ("int64", None, 28, "uniform", True, 0, 64),
     "sortpairs_u32_u32_2^28_uniform": ("uint32", "uint32", 28, "uniform", False, 0, 32),
+    # skew rows of SURVEY.md 10.16 (reported for "no pathological slowdown", not headline numbers)
+    "sortkeys_u32_2^28_entropy0.201": ("uint32", None, 28, "entropy5", False, 0, 32),
+    "sortkeys_u32_2^28_equal": ("uint32", None, 28, "equal", False, 0, 32),
+    "sortkeys_u32_2^28_few16": ("uint32", None, 28, "few16", False, 0, 32),
+    "sortkeys_u32_2^28_sorted": ("uint32", None, 28, "sorted", False, 0, 32),
 }
 DEFAULT_1GPU = "sortkeys_u32_2^28_uniform"
 DEFAULT_NGPU = "dist_sortpairs_u32_u32_2^28_per_gpu"
@@ -222,6 +227,15 @@ def make_device_input(torch, np, name):
     if dist.startswith("entropy"):
         for _ in range(int(dist[7:]) - 1):
             raw &= torch.randint(-(2**63), 2**63 - 1, (words,), dtype=torch.int64, device="cuda", generator=g)
+    if dist == "equal":
+        raw.fill_(0x0123456701234567)
+    elif dist.startswith("few"):
+        k = int(dist[3:])
+        pool = torch.randint(-(2**63), 2**63 - 1, (k,), dtype=torch.int64, device="cuda", generator=g)
+        idx = torch.randint(0, k, (n,), dtype=torch.int64, device="cuda", generator=g)
+        raw = pool.view(torch.int32 if kb == 4 else torch.int64)[:k][idx].contiguous().view(torch.int64)
+    elif dist == "sorted":
+        raw = torch.sort(raw.view(torch.int32 if kb == 4 else torch.int64)).values.view(torch.int64)
     keys = raw.view(torch.uint8)
     vals = None
     if vdt is not None:
