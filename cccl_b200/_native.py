@@ -26,6 +26,7 @@ EXPORTS = (
     "b200rs_set_config",
     "b200rs_set_portion_items",
     "b200rs_set_force_big",
+    "b200rs_set_single_tile",
     "b200rs_describe_config",
     "b200rs_timing_enable",
     "b200rs_timing_read",
@@ -77,6 +78,8 @@ def lib() -> ctypes.CDLL:
         l.b200rs_set_portion_items.argtypes = [ctypes.c_ulonglong]
         l.b200rs_set_force_big.restype = i32
         l.b200rs_set_force_big.argtypes = [i32]
+        l.b200rs_set_single_tile.restype = i32
+        l.b200rs_set_single_tile.argtypes = [i32]
         l.b200rs_describe_config.restype = i32
         l.b200rs_describe_config.argtypes = [i32, i32, i32, ctypes.c_char_p, ctypes.c_size_t]
         l.b200rs_timing_enable.restype = i32
@@ -105,7 +108,7 @@ def sort_raw(d_temp: int, temp_bytes: int, keys_in: int, keys_out: int, vals_in:
     return nbytes.value, selector.value
 
 
-OP_NAMES = ("memset", "histogram", "scan", "onesweep", "copy")
+OP_NAMES = ("memset", "histogram", "scan", "onesweep", "copy", "single_tile")
 
 
 def timing_read():

@@ -33,6 +33,12 @@ cudaError_t launch_histogram(
   int end_bit, const KeyXform& xf, int sm_count, cudaStream_t stream);
 cudaError_t launch_scan_bins(unsigned long long* bins, int passes, cudaStream_t stream);
 
+// whole sort in one CTA (single_tile.cu); capacity in items for the given key / value widths
+unsigned long long single_tile_capacity(int key_bytes, int value_bytes);
+cudaError_t launch_single_tile(
+  const void* keys_in, void* keys_out, const void* vals_in, void* vals_out, unsigned long long n, int key_bytes,
+  int value_bytes, int begin_bit, int end_bit, const KeyXform& xf, cudaStream_t stream);
+
 cudaError_t launch_splitter_ranks(
   const void* sorted_keys, unsigned long long n, int key_bytes, const KeyXform& xf, const void* splitters,
   int num_splitters, unsigned long long* lt, unsigned long long* eq, cudaStream_t stream);

@@ -22,6 +22,7 @@ namespace b200rs
 static std::atomic<int> g_config_override{-1};
 static std::atomic<unsigned long long> g_portion_override{0};
 static std::atomic<bool> g_force_big{false};
+static std::atomic<bool> g_no_single_tile{false};
 static thread_local int t_last_launches = 0;
 
 // Optional per-op device timing (bench.py's roofline leg): when enabled, an event is recorded on the stream before
@@ -39,7 +40,8 @@ enum OpKind
   OP_HISTOGRAM = 1,
   OP_SCAN      = 2,
   OP_ONESWEEP  = 3,
-  OP_COPY      = 4
+  OP_COPY      = 4,
+  OP_SINGLE    = 5
 };
 
 static void mark_op(cudaStream_t stream, int kind)
@@ -220,6 +222,13 @@ B200RS_API int b200rs_set_force_big(int on)
   return 0;
 }
 
+// diagnostic: route inputs of at most one tile through the general path as well (tests compare both)
+B200RS_API int b200rs_set_single_tile(int on)
+{
+  g_no_single_tile.store(on == 0, std::memory_order_relaxed);
+  return 0;
+}
+
 int b200rs_describe_config(int key_bytes, int value_bytes, int config_index, char* buf, size_t buf_len)
 {
   int count                 = 0;
@@ -396,6 +405,28 @@ int b200rs_sort(
       *selector = 1;
     }
     return int(e);
+  }
+
+  // at most one tile: the whole sort is one launch of one CTA, no temp storage
+  // (dispatch_radix_sort.cuh:1980, kernel_radix_sort.cuh:330-434)
+  if (num_items <= single_tile_capacity(key_bytes, value_bytes) && !g_no_single_tile.load(std::memory_order_relaxed))
+  {
+    if (query)
+    {
+      *temp_storage_bytes = 1;
+      return 0;
+    }
+    const KeyXform sxf =
+      make_xform(key_kind, key_bytes, descending, num_items <= reference_single_tile_items(key_bytes, value_bytes));
+    mark_op(stream, OP_SINGLE);
+    const cudaError_t se = launch_single_tile(d_keys_in, d_keys_out, d_values_in, d_values_out, num_items, key_bytes,
+                                              value_bytes, begin_bit, end_bit, sxf, stream);
+    mark_end(stream);
+    if (se == cudaSuccess && selector != nullptr)
+    {
+      *selector = 1;
+    }
+    return int(se);
   }
 
   const OnesweepConfig* cfg = pick_config(key_bytes, value_bytes);

@@ -260,6 +260,11 @@ B200RS_API int b200rs_set_portion_items(unsigned long long items);
  * reference's 64-bit OffsetT case, detail/choose_offset.cuh:35-52) so tests can exercise them at small N. */
 B200RS_API int b200rs_set_force_big(int on);
 
+/* Diagnostic: 0 routes inputs of at most one tile (which normally take the single-CTA kernel that replaces
+ * DeviceRadixSortSingleTileKernel, kernel_radix_sort.cuh:330-434) through the general multi-kernel path as well, so
+ * tests can compare the two; 1 (default) restores the single-CTA kernel. */
+B200RS_API int b200rs_set_single_tile(int on);
+
 /* Human-readable description of configuration `config_index` for (key_bytes, value_bytes); returns the number of
  * configurations available when config_index < 0.  buf may be NULL. */
 B200RS_API int b200rs_describe_config(int key_bytes, int value_bytes, int config_index, char* buf, size_t buf_len);

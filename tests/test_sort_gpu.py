@@ -129,6 +129,40 @@ def test_value_widths(kdtype, vdtype):
         check_pairs(k, v, api="double", descending=True)
 
 
+@pytest.mark.parametrize("kdtype", [np.uint8, np.int16, np.uint32, np.float32, np.int64, np.float64])
+def test_single_tile_kernel_and_general_path_agree(kdtype):
+    """Inputs of at most one tile take the single-CTA kernel (reference: DeviceRadixSortSingleTileKernel,
+    kernel_radix_sort.cuh:330-434, chosen at dispatch_radix_sort.cuh:1980).  Sizes straddle its capacities
+    (5120 / 2560 / 1280 items for <= 4 / 8 / 16-byte items); the same inputs are also pushed through the general
+    multi-kernel path (diagnostic switch) -- both must equal the oracle, one launch vs several."""
+    from cccl_b200 import _native
+
+    lib = _native.lib()
+    bits = np.dtype(kdtype).itemsize * 8
+    sizes = [1, 2, 33, 1000, 1279, 1280, 1281, 2559, 2560, 2561, 4864, 5119, 5120, 5121]
+    for vdtype in (None, np.uint8, np.uint32, np.uint64, V16):
+        for n in sizes:
+            k = make_keys("few256" if n % 2 else "uniform", n, kdtype, seed=n)
+            if np.dtype(kdtype).kind == "f":
+                k[::7] = -0.0
+                k[::11] = 0.0
+            v = make_values(n, vdtype) if vdtype is not None else None
+            dom = max(np.dtype(kdtype).itemsize, np.dtype(vdtype).itemsize if vdtype is not None else 0)
+            cap = 256 * (20 if dom <= 4 else 10 if dom <= 8 else 5)
+            for kw in (dict(), dict(descending=True, api="double"), dict(begin_bit=bits // 4, end_bit=bits - 3,
+                                                                          descending=True)):
+                info = check_pairs(k, v, **kw) if v is not None else check_keys(k, **kw)
+                assert (info["launches"] == 1) == (n <= cap), (n, cap, info)
+                if n <= cap:
+                    assert info["temp_bytes"] == 1
+                    try:
+                        lib.b200rs_set_single_tile(0)
+                        info2 = check_pairs(k, v, **kw) if v is not None else check_keys(k, **kw)
+                        assert info2["launches"] > 1
+                    finally:
+                        lib.b200rs_set_single_tile(1)
+
+
 def test_double_buffer_selector_and_pass_parity():
     # result is wherever selector says (catch2_test_device_radix_sort_keys.cu:441-446)
     k = make_keys("uniform", 50_000, np.uint32, seed=8)
