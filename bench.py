@@ -124,8 +124,9 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_reference_run(steps, warmup, log2n=24, threads=None):
-    """thrust::sort (OMP) of the unmodified reference on a bounded sample: 2^24 uniform u32 keys per step."""
+def cpu_reference_run(steps, warmup, log2n=24, threads=None, pairs=False):
+    """thrust::sort / sort_by_key (OMP) of the unmodified reference on a bounded sample: 2^24 uniform u32 keys
+    (+ u32 values when `pairs`, the multi-GPU arm's workload) per step."""
     import numpy as np
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -134,6 +135,7 @@ def cpu_reference_run(steps, warmup, log2n=24, threads=None):
 
     n = 1 << log2n
     keys = make_keys("uniform", n, np.uint32, seed=42)
+    vals = np.arange(n, dtype=np.uint32) if pairs else None
     lib = ref_thrust("omp")
     kind = "reference"
     if lib is None:
@@ -145,7 +147,7 @@ def cpu_reference_run(steps, warmup, log2n=24, threads=None):
             cores = threads
         times = []
         for i in range(warmup + steps):
-            _, secs = ref_thrust_sort(keys, backend="omp")
+            secs = ref_thrust_sort(keys, vals, backend="omp")[-1]
             if i >= warmup:
                 times.append(secs)
     else:
@@ -153,7 +155,7 @@ def cpu_reference_run(steps, warmup, log2n=24, threads=None):
         times = []
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            oracle_sort(keys)
+            oracle_sort(keys, vals) if pairs else oracle_sort(keys)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     total = sum(times)
@@ -162,8 +164,8 @@ def cpu_reference_run(steps, warmup, log2n=24, threads=None):
         "unit": "Gkeys/s",
         "cores": cores,
         "kind": kind,
-        "sample": f"thrust::sort (OMP backend) of 2^{log2n} uniform u32 keys per step, {len(times)} steps, "
-                  f"sort call only (host copies excluded)",
+        "sample": f"thrust::{'sort_by_key' if pairs else 'sort'} (OMP backend) of 2^{log2n} uniform u32 keys"
+                  f"{' + u32 values' if pairs else ''} per step, {len(times)} steps, sort call only (host copies excluded)",
         "ms_per_step": total / len(times) * 1e3,
     }
 
@@ -193,7 +195,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 8))
-    r = cpu_reference_run(steps, min(args.warmup, 1))
+    r = cpu_reference_run(steps, min(args.warmup, 1), pairs=args.gpus > 1)
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -209,7 +211,8 @@ def run_reference(args):
         "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": DEFAULT_1GPU if args.gpus == 1 else DEFAULT_NGPU,
-                   "reference_arm": "thrust::sort, THRUST_DEVICE_SYSTEM=OMP, host cores, bounded sample 2^24 keys/step"},
+                   "reference_arm": ("thrust::sort_by_key" if args.gpus > 1 else "thrust::sort")
+                   + ", THRUST_DEVICE_SYSTEM=OMP, host cores, bounded sample 2^24 items/step"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
