@@ -264,7 +264,7 @@ int b200rs_digit_histogram(
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (key_kind < 0 || key_kind > 2 || (key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8)
       || begin_bit < 0 || end_bit < begin_bit || end_bit > key_bytes * 8 || d_bins == nullptr
-      || (key_kind == 2 && key_bytes < 4))
+      || (key_kind == 2 && key_bytes < 2))
   {
     return int(cudaErrorInvalidValue);
   }
@@ -304,7 +304,7 @@ int b200rs_splitter_ranks(
   uint64_t* d_eq,
   b200rs_stream_t stream_)
 {
-  if (key_kind < 0 || key_kind > 2 || num_splitters < 0 || (key_kind == 2 && key_bytes < 4))
+  if (key_kind < 0 || key_kind > 2 || num_splitters < 0 || (key_kind == 2 && key_bytes < 2))
   {
     return int(cudaErrorInvalidValue);
   }
@@ -343,7 +343,7 @@ int b200rs_sort(
   if ((key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8)
       || (value_bytes != 0 && value_bytes != 1 && value_bytes != 2 && value_bytes != 4 && value_bytes != 8
           && value_bytes != 16)
-      || (key_kind == 2 && key_bytes < 4))
+      || (key_kind == 2 && key_bytes < 2))
   {
     return int(cudaErrorNotSupported);
   }
@@ -629,7 +629,7 @@ int b200rs_partition_by_splitters(
   t_last_launches     = 0;
   t_events_used       = 0;
   if (temp_storage_bytes == nullptr || key_kind < 0 || key_kind > 2 || num_splitters < 0 || num_splitters > 15
-      || (key_kind == 2 && key_bytes < 4))
+      || (key_kind == 2 && key_bytes < 2))
   {
     return int(cudaErrorInvalidValue);
   }

@@ -15,7 +15,7 @@ cudaError_t launch_onesweep(const PassArgs& args, unsigned grid, cudaStream_t st
   using L = OnesweepSmem<U, VB, NT, IPT, OPT>;
   // the -0.0 == +0.0 digit rule is compiled in only where it can matter: floating-point keys (4/8 bytes);
   // 64-bit output offsets only for arrays of 2^32 items and more
-  constexpr bool CAN_FLOAT = sizeof(U) >= 4;
+  constexpr bool CAN_FLOAT = sizeof(U) >= 2; // half / bfloat16, float, double
   const bool flt           = CAN_FLOAT && args.xf.float_mask != 0;
   auto kernel              = onesweep_kernel<U, VB, NT, IPT, RANK, MINB, OPT, false, false>;
   if (OPT & OPT_BUCKET)
@@ -69,7 +69,7 @@ template <class U, int VB, int NT, int IPT, int MINB, int LBW>
 cudaError_t launch_onesweep_tma(const PassArgs& args, unsigned grid, cudaStream_t stream)
 {
   using L = TmaSmem<U, VB, NT, IPT>;
-  constexpr bool CAN_FLOAT = sizeof(U) >= 4;
+  constexpr bool CAN_FLOAT = sizeof(U) >= 2; // half / bfloat16, float, double
   const bool flt           = CAN_FLOAT && args.xf.float_mask != 0;
   auto kernel              = onesweep_tma_kernel<U, VB, NT, IPT, MINB, LBW, false>;
   if (flt)

@@ -344,7 +344,7 @@ int b200rs_select_histogram(
     return int(cudaErrorInvalidValue);
   }
   if (key_kind < 0 || key_kind > 2 || (key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8)
-      || (key_kind == 2 && key_bytes < 4) || num_prefixes < 0 || num_prefixes > MAX_SPLITTERS || round < 0
+      || (key_kind == 2 && key_bytes < 2) || num_prefixes < 0 || num_prefixes > MAX_SPLITTERS || round < 0
       || round >= key_bytes || d_hist == nullptr || (num_prefixes > 0 && d_prefixes == nullptr))
   {
     return int(cudaErrorInvalidValue);
@@ -398,7 +398,7 @@ int b200rs_bucket_ids(
 {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (key_kind < 0 || key_kind > 2 || (key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8)
-      || (key_kind == 2 && key_bytes < 4) || num_splitters < 0 || num_splitters > MAX_SPLITTERS
+      || (key_kind == 2 && key_bytes < 2) || num_splitters < 0 || num_splitters > MAX_SPLITTERS
       || (num_splitters > 0 && h_splitters == nullptr) || (num_items > 0 && d_ids == nullptr))
   {
     return int(cudaErrorInvalidValue);

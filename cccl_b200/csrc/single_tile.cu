@@ -208,7 +208,7 @@ static cudaError_t launch_st(const SingleTileArgs& a, cudaStream_t stream)
 {
   constexpr int IPT        = SingleTileShape<U, VB>::IPT;
   using L                  = SingleTileSmem<U, VB, IPT>;
-  constexpr bool CAN_FLOAT = sizeof(U) >= 4;
+  constexpr bool CAN_FLOAT = sizeof(U) >= 2; // half / bfloat16, float, double
   auto kernel              = single_tile_kernel<U, VB, IPT, false>;
   if (CAN_FLOAT && a.xf.float_mask != 0)
   {

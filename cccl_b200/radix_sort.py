@@ -47,6 +47,9 @@ def _torch_np_dtype(t):
         _TORCH_TO_NP = {
             torch.uint8: np.uint8, torch.int8: np.int8, torch.int16: np.int16, torch.int32: np.int32,
             torch.int64: np.int64, torch.float32: np.float32, torch.float64: np.float64, torch.bool: np.bool_,
+            # 16-bit floats: only (floating point, 2 bytes) matters to the kernels -- half and bfloat16 share the
+            # sign-magnitude layout the key transform works on (reference: util_type.cuh:1017-1095)
+            torch.float16: np.float16, torch.bfloat16: np.float16,
         }
         for name, npdt in (("uint16", np.uint16), ("uint32", np.uint32), ("uint64", np.uint64)):
             if hasattr(torch, name):
@@ -77,8 +80,6 @@ def _describe(arr):
 
 def key_kind_of(dtype: np.dtype) -> int:
     if dtype.kind == "f":
-        if dtype.itemsize < 4:
-            raise TypeError("16-bit float keys are not supported yet")
         return _native.KEY_FLOAT
     if dtype.kind == "i":
         return _native.KEY_INT

@@ -49,7 +49,9 @@ typedef enum b200rs_key_kind
   B200RS_KEY_UINT  = 0, /* unsigned integers, bool, char: identity            */
   B200RS_KEY_INT   = 1, /* two's complement signed: flip the sign bit         */
   B200RS_KEY_FLOAT = 2  /* IEEE-754: negative -> ~x, else flip the sign bit;  */
-                        /* -0.0 and +0.0 compare equal (stable), NaNs by bits */
+                        /* -0.0 and +0.0 compare equal (stable), NaNs by bits. */
+                        /* key_bytes 2 (__half or __nv_bfloat16: same sign-     */
+                        /* magnitude layout, util_type.cuh:1017-1095), 4 or 8   */
 } b200rs_key_kind;
 
 #define B200RS_VERSION 100 /* 0.1.0 */

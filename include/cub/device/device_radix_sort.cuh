@@ -25,6 +25,8 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstddef>
 #include <cstdint>
@@ -69,14 +71,20 @@ enum class SortOrder
 namespace detail
 {
 // Traits<T>::CATEGORY of the reference (util_type.cuh:857-963) reduced to what the transform needs.
+// 16-bit floating-point keys (reference: __can_use_radix_sort, device_radix_sort.cuh:51-57; NumericTraits<__half>,
+// NumericTraits<__nv_bfloat16>, util_type.cuh:1017-1095): same sign-magnitude transform on a 16-bit pattern.
+template <class K>
+struct b200rs_is_float16 : std::integral_constant<bool, std::is_same<K, __half>::value || std::is_same<K, __nv_bfloat16>::value>
+{};
+
 template <class KeyT>
 constexpr int b200rs_key_kind_of()
 {
   using K = std::remove_cv_t<KeyT>;
-  static_assert(std::is_arithmetic<K>::value,
+  static_assert(std::is_arithmetic<K>::value || b200rs_is_float16<K>::value,
                 "this drop-in covers arithmetic keys; decomposer / user-defined keys are not built (SURVEY 8f)");
   static_assert(sizeof(K) == 1 || sizeof(K) == 2 || sizeof(K) == 4 || sizeof(K) == 8, "key width must be 1/2/4/8");
-  return std::is_floating_point<K>::value ? B200RS_KEY_FLOAT
+  return (std::is_floating_point<K>::value || b200rs_is_float16<K>::value) ? B200RS_KEY_FLOAT
        : (std::is_signed<K>::value && !std::is_same<K, bool>::value) ? B200RS_KEY_INT
                                                                      : B200RS_KEY_UINT;
 }

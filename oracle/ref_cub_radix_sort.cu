@@ -8,7 +8,9 @@
 //
 // usage: ref_cub_radix_sort sort  <ktype> <vbytes> <n> <desc> <begin_bit> <end_bit> <keys.bin> <vals.bin|-> <out_keys.bin> <out_vals.bin|->
 //        ref_cub_radix_sort bench <ktype> <vbytes> <log2n> <desc> <begin_bit> <end_bit> <and_rounds> <iters>
-//   ktype in {u8,i8,u16,i16,u32,i32,f32,u64,i64,f64}; vbytes in {0,4,8}
+//   ktype in {u8,i8,u16,i16,f16,bf16,u32,i32,f32,u64,i64,f64}; vbytes in {0,4,8}
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cstdint>
@@ -195,6 +197,8 @@ int main(int argc, char** argv)
   if (kt == "i16") return by_value<int16_t>(argc, argv);
   if (kt == "u32") return by_value<uint32_t>(argc, argv);
   if (kt == "i32") return by_value<int32_t>(argc, argv);
+  if (kt == "f16") return by_value<__half>(argc, argv);
+  if (kt == "bf16") return by_value<__nv_bfloat16>(argc, argv);
   if (kt == "f32") return by_value<float>(argc, argv);
   if (kt == "u64") return by_value<uint64_t>(argc, argv);
   if (kt == "i64") return by_value<int64_t>(argc, argv);

@@ -24,7 +24,7 @@ def to_host(t: torch.Tensor, dtype, n) -> np.ndarray:
 
 
 def gpu_sort(keys: np.ndarray, values: np.ndarray | None = None, *, descending=False, begin_bit=0, end_bit=None,
-             api="pointer", stream=None, check_input_untouched=True, temp_misalign=0):
+             api="pointer", stream=None, check_input_untouched=True, temp_misalign=0, kind=None):
     """Sort through b200rs_sort.  api='pointer' (is_overwrite_okay=0) or 'double' (DoubleBuffer semantics).
     Returns (keys_out[, values_out], info dict)."""
     n = keys.shape[0]
@@ -32,7 +32,7 @@ def gpu_sort(keys: np.ndarray, values: np.ndarray | None = None, *, descending=F
     vb = values.dtype.itemsize if values is not None else 0
     if end_bit is None:
         end_bit = kb * 8
-    kind = key_kind_of(kdt)
+    kind = key_kind_of(kdt) if kind is None else kind  # override: e.g. bfloat16 bit patterns held in uint16
     d_k0 = to_dev(keys)
     d_k1 = torch.empty_like(d_k0)
     d_v0 = to_dev(values)

@@ -56,7 +56,7 @@ def test_empty_problem_needs_one_byte():
     ((10, 4, 3, 0, 32, False), 801),    # unsupported value width
     ((10, 4, 0, 8, 40, False), 1),      # end_bit beyond the key
     ((10, 4, 0, 9, 8, False), 1),       # begin > end
-    ((10, 2, 0, 0, 16, False, 2), 801), # 16-bit float keys
+    ((10, 1, 0, 0, 8, False, 2), 801),  # 8-bit float keys (16-bit half / bfloat16 keys are supported)
 ])
 def test_bad_arguments(args, code):
     with pytest.raises(_native.B200RSError) as e:

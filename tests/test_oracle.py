@@ -101,3 +101,22 @@ def test_committed_golden_fixtures():
             assert np.array_equal(got[1], z["vals_out"]), f
         else:
             assert np.array_equal(got.view(np.uint8), z["keys_out"].view(np.uint8)), f
+
+
+def test_16_bit_float_keys_in_the_oracle():
+    """half keys (reference: util_type.cuh:1017-1095, device_radix_sort.cuh:51-57): the generic transform on a 16-bit
+    pattern.  Checked against numpy's own float16 ordering on NaN-free data, plus +-0 stability and NaN placement."""
+    rng = np.random.default_rng(5)
+    k = rng.standard_normal(20_000).astype(np.float16)
+    k[::13] = np.float16(-0.0)
+    k[::17] = np.float16(0.0)
+    v = np.arange(k.size, dtype=np.uint32)
+    for desc in (False, True):
+        ok, ov = oracle_sort(k, v, descending=desc)
+        want = np.sort(k, kind="stable")
+        assert np.array_equal(ok.astype(np.float32), want[::-1].astype(np.float32) if desc else want.astype(np.float32))
+        z = ok == 0  # both zeros tie: they keep input order (values increasing inside the run of zeros)
+        assert (np.diff(ov[z].astype(np.int64)) > 0).all()
+    bits = np.array([0x7E00, 0xFE00, 0x3C00, 0xBC00, 0x7C00, 0xFC00], dtype=np.uint16).view(np.float16)
+    ok = oracle_sort(bits)
+    assert ok.view(np.uint16).tolist() == [0xFE00, 0xFC00, 0xBC00, 0x3C00, 0x7C00, 0x7E00]  # -NaN -inf -1 1 +inf +NaN

@@ -14,7 +14,8 @@ from oracle_lib import oracle_histogram, oracle_sort
 
 pytestmark = pytest.mark.gpu
 
-KEY_DTYPES = [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.uint64, np.int64, np.float64]
+KEY_DTYPES = [np.uint8, np.int8, np.uint16, np.int16, np.float16, np.uint32, np.int32, np.float32, np.uint64, np.int64,
+              np.float64]
 
 
 def check_keys(k, **kw):
@@ -87,16 +88,16 @@ def test_bit_windows(dtype):
     check_keys(k, begin_bit=3, end_bit=4)
 
 
-@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("dtype", [np.float16, np.float32, np.float64])
 def test_signed_zeros_and_nans(dtype):
-    udt = np.uint32 if dtype == np.float32 else np.uint64
+    udt = {np.float16: np.uint16, np.float32: np.uint32, np.float64: np.uint64}[dtype]
     n = 50_000
     rng = np.random.default_rng(2)
     k = rng.standard_normal(n).astype(dtype)
     k[rng.integers(0, n, n // 5)] = 0.0
     k[rng.integers(0, n, n // 5)] = -0.0
     nanbits = make_keys("uniform", n // 10, dtype, seed=4).view(udt)
-    expmask = udt(0x7F800000) if dtype == np.float32 else udt(0x7FF0000000000000)
+    expmask = udt({np.float16: 0x7C00, np.float32: 0x7F800000, np.float64: 0x7FF0000000000000}[dtype])
     idx = rng.integers(0, n, n // 10)
     k.view(udt)[idx] = nanbits | expmask | udt(1)  # +-NaN with random payloads
     k[rng.integers(0, n, 100)] = np.inf

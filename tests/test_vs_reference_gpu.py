@@ -16,16 +16,16 @@ pytestmark = pytest.mark.gpu
 BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_cub_radix_sort")
 KT = {np.dtype(np.uint8): "u8", np.dtype(np.int8): "i8", np.dtype(np.uint16): "u16", np.dtype(np.int16): "i16",
       np.dtype(np.uint32): "u32", np.dtype(np.int32): "i32", np.dtype(np.float32): "f32",
-      np.dtype(np.uint64): "u64", np.dtype(np.int64): "i64", np.dtype(np.float64): "f64"}
+      np.dtype(np.uint64): "u64", np.dtype(np.int64): "i64", np.dtype(np.float64): "f64", np.dtype(np.float16): "f16"}
 
 
-def ref_cub_sort(keys, values, descending, begin_bit, end_bit):
+def ref_cub_sort(keys, values, descending, begin_bit, end_bit, ktype=None):
     with tempfile.TemporaryDirectory() as d:
         kf, vf, ko, vo = (os.path.join(d, x) for x in ("k.bin", "v.bin", "ko.bin", "vo.bin"))
         keys.tofile(kf)
         if values is not None:
             values.tofile(vf)
-        cmd = [BIN, "sort", KT[keys.dtype], str(values.dtype.itemsize if values is not None else 0), str(keys.size),
+        cmd = [BIN, "sort", ktype or KT[keys.dtype], str(values.dtype.itemsize if values is not None else 0), str(keys.size),
                str(int(descending)), str(begin_bit), str(end_bit), kf, vf if values is not None else "-", ko,
                vo if values is not None else "-"]
         subprocess.run(cmd, check=True, timeout=300)
@@ -61,3 +61,20 @@ def test_bit_identical_to_reference_cub(kdtype, vdtype, dist, n, desc, window):
         gk, gv, _ = gpu_sort(k, v, descending=desc, begin_bit=b, end_bit=e)
         assert_same_bits(gv, rv, "values vs reference CUB")
     assert_same_bits(gk, rk, "keys vs reference CUB")
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="oracle/_ref/ref_cub_radix_sort not built")
+@pytest.mark.parametrize("ktype", ["f16", "bf16"])
+@pytest.mark.parametrize("n,desc,window", [(300_001, False, None), (4000, True, (3, 14)), (1 << 20, True, None)])
+def test_16_bit_float_keys_bit_identical_to_reference_cub(ktype, n, desc, window):
+    """__half / __nv_bfloat16 keys (reference: device_radix_sort.cuh:51-57, util_type.cuh:1017-1095): the same
+    sign-magnitude transform on 16-bit patterns, every bit pattern included (NaNs, infinities, both zeros)."""
+    bits = make_keys("uniform", n, np.uint16, seed=5)
+    bits[::97] = 0x8000  # -0.0
+    bits[::89] = 0x0000  # +0.0
+    v = make_values(n, np.uint32)
+    b, e = window if window else (0, 16)
+    rk, rv = ref_cub_sort(bits, v, desc, b, e, ktype=ktype)
+    gk, gv, _ = gpu_sort(bits, v, descending=desc, begin_bit=b, end_bit=e, kind=2)
+    assert_same_bits(gk, rk, f"{ktype} keys vs cub n={n}")
+    assert_same_bits(gv, rv, f"{ktype} values vs cub n={n}")
