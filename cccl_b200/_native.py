@@ -22,6 +22,7 @@ EXPORTS = (
     "b200rs_select_histogram",
     "b200rs_bucket_ids",
     "b200rs_partition_by_splitters",
+    "b200rs_partition_to_peers",
     "b200rs_last_launch_count",
     "b200rs_set_config",
     "b200rs_set_portion_items",
@@ -70,6 +71,10 @@ def lib() -> ctypes.CDLL:
         l.b200rs_partition_by_splitters.restype = i32
         l.b200rs_partition_by_splitters.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, vp, vp, u64, i32, i32,
                                                     i32, i32, ctypes.POINTER(u64), i32, ctypes.POINTER(u64), vp]
+        pu64 = ctypes.POINTER(u64)
+        l.b200rs_partition_to_peers.restype = i32
+        l.b200rs_partition_to_peers.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, u64, i32, i32, i32, i32,
+                                                pu64, i32, pu64, i32, pu64, pu64, pu64, vp]
         l.b200rs_last_launch_count.restype = i32
         l.b200rs_last_launch_count.argtypes = []
         l.b200rs_set_config.restype = i32

@@ -207,6 +207,21 @@ __device__ __forceinline__ uint32_t lanemask_lt()
   return r;
 }
 
+// Bucket mode with remote destinations (multi-GPU: the partition pass stores straight into the receive buffers of the
+// destination GPUs over NVLink).  The partitioned order is cut into `num_dests` contiguous segments, segment r going to
+// rank r; every pointer is biased so that the element with partitioned index idx is stored at ptr + idx * item size.
+// bucket_dst_*[b] is the pointer of the one rank a bucket goes to, or 0 when a segment boundary falls inside it.
+struct PeerTable
+{
+  uint32_t num_dests;
+  uint32_t pad;
+  unsigned long long bucket_dst_keys[32];
+  unsigned long long bucket_dst_vals[32];
+  unsigned long long rank_dst_keys[16];
+  unsigned long long rank_dst_vals[16];
+  uint32_t seg_end[16]; // seg_end[r] = first partitioned index that does NOT go to ranks <= r
+};
+
 // Everything one digit pass over one portion needs (type-erased; kernels cast).
 struct PassArgs
 {
@@ -233,6 +248,7 @@ struct PassArgs
   // (bit-ordered values, strictly increasing): 2 * #{splitters below the key} + [key equals a splitter]
   int num_splitters;
   unsigned long long splitters[15];
+  const PeerTable* peer; // bucket mode: remote destinations (device memory), or nullptr for keys_out / vals_out
 };
 
 } // namespace b200rs

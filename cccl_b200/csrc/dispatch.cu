@@ -590,6 +590,7 @@ int b200rs_sort(
       a.big          = (num_items >> 32) != 0 || g_force_big.load(std::memory_order_relaxed);
       a.xf           = xf;
       a.num_splitters = 0;
+      a.peer          = nullptr;
       mark_op(stream, OP_ONESWEEP);
       e = cfg->launch(a, tiles, stream);
       if (e != cudaSuccess)
@@ -608,7 +609,12 @@ int b200rs_sort(
   return 0;
 }
 
-int b200rs_partition_by_splitters(
+} // extern "C"
+
+// The partition pass (one onesweep launch in bucket mode).  num_dests == 0: results go to d_keys_out / d_values_out;
+// otherwise the partitioned order is cut at h_segment_ends and segment r is stored through the (biased) pointers
+// h_rank_dst_keys[r] / h_rank_dst_vals[r] -- peer-mapped receive buffers of the destination GPUs.
+static int partition_impl(
   void* d_temp_storage,
   size_t* temp_storage_bytes,
   const void* d_keys_in,
@@ -623,13 +629,17 @@ int b200rs_partition_by_splitters(
   const uint64_t* h_splitters,
   int num_splitters,
   const uint64_t* h_bucket_offsets,
+  int num_dests,
+  const uint64_t* h_segment_ends,
+  const uint64_t* h_rank_dst_keys,
+  const uint64_t* h_rank_dst_vals,
   b200rs_stream_t stream_)
 {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   t_last_launches     = 0;
   t_events_used       = 0;
   if (temp_storage_bytes == nullptr || key_kind < 0 || key_kind > 2 || num_splitters < 0 || num_splitters > 15
-      || (key_kind == 2 && key_bytes < 2))
+      || (key_kind == 2 && key_bytes < 2) || num_dests < 0 || num_dests > 16)
   {
     return int(cudaErrorInvalidValue);
   }
@@ -657,6 +667,9 @@ int b200rs_partition_by_splitters(
   off += 256;
   const size_t off_lb = off;
   off += align_up(size_t(tiles > 0 ? tiles : 1) * RADIX * sizeof(uint32_t), 256);
+  const size_t control = off; // everything up to here is zeroed
+  const size_t off_peer = off;
+  off += align_up(sizeof(PeerTable), 256);
   const size_t total = off + 255;
   if (query)
   {
@@ -671,8 +684,12 @@ int b200rs_partition_by_splitters(
   {
     return 0;
   }
-  if (d_keys_in == nullptr || d_keys_out == nullptr || (value_bytes > 0 && (d_values_in == nullptr || d_values_out == nullptr))
-      || (num_splitters > 0 && h_splitters == nullptr) || h_bucket_offsets == nullptr)
+  const bool remote = num_dests > 0;
+  if (d_keys_in == nullptr || (value_bytes > 0 && d_values_in == nullptr) || (num_splitters > 0 && h_splitters == nullptr)
+      || h_bucket_offsets == nullptr
+      || (!remote && (d_keys_out == nullptr || (value_bytes > 0 && d_values_out == nullptr)))
+      || (remote && (h_rank_dst_keys == nullptr || (value_bytes > 0 && h_rank_dst_vals == nullptr)
+                     || (num_dests > 1 && h_segment_ends == nullptr))))
   {
     return int(cudaErrorInvalidValue);
   }
@@ -683,10 +700,43 @@ int b200rs_partition_by_splitters(
     return e;
   }
   mark_op(stream, OP_MEMSET);
-  cudaError_t e = cudaMemsetAsync(base, 0, off, stream);
+  cudaError_t e = cudaMemsetAsync(base, 0, control, stream);
   if (e != cudaSuccess)
   {
     return int(e);
+  }
+  if (remote)
+  {
+    // which rank each bucket goes to (0 = a segment boundary falls inside it: resolved per item in the kernel)
+    PeerTable pt;
+    memset(&pt, 0, sizeof(pt));
+    pt.num_dests = uint32_t(num_dests);
+    for (int r = 0; r < num_dests; ++r)
+    {
+      pt.rank_dst_keys[r] = h_rank_dst_keys[r];
+      pt.rank_dst_vals[r] = value_bytes > 0 ? h_rank_dst_vals[r] : 0;
+      pt.seg_end[r]       = r + 1 < num_dests ? uint32_t(h_segment_ends[r]) : 0xffffffffu;
+    }
+    const int nb = 2 * num_splitters + 1;
+    for (int b = 0; b < nb; ++b)
+    {
+      const uint64_t lo = h_bucket_offsets[b];
+      const uint64_t hi = b + 1 < nb ? h_bucket_offsets[b + 1] : num_items;
+      int r_lo = 0, r_hi = 0;
+      for (int r = 0; r + 1 < num_dests; ++r)
+      {
+        r_lo += h_segment_ends[r] <= lo ? 1 : 0;
+        r_hi += (hi > lo && h_segment_ends[r] < hi) ? 1 : 0;
+      }
+      const bool one_rank     = hi <= lo || r_lo == r_hi;
+      pt.bucket_dst_keys[b]   = one_rank ? pt.rank_dst_keys[r_lo] : 0;
+      pt.bucket_dst_vals[b]   = one_rank ? pt.rank_dst_vals[r_lo] : 0;
+    }
+    e = cudaMemcpyAsync(base + off_peer, &pt, sizeof(pt), cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess)
+    {
+      return int(e);
+    }
   }
   // exclusive bucket offsets (2 * num_splitters + 1 of them) -> the pass's per-digit output offsets
   e = cudaMemcpyAsync(base + off_bins, h_bucket_offsets, size_t(2 * num_splitters + 1) * sizeof(uint64_t),
@@ -720,10 +770,63 @@ int b200rs_partition_by_splitters(
   {
     a.splitters[i] = h_splitters[i];
   }
+  a.peer = remote ? reinterpret_cast<const PeerTable*>(base + off_peer) : nullptr;
   mark_op(stream, OP_ONESWEEP);
   e = cfg->launch_bucket(a, unsigned(tiles), stream);
   mark_end(stream);
   return int(e);
+}
+
+extern "C" {
+
+int b200rs_partition_by_splitters(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int descending,
+  const uint64_t* h_splitters,
+  int num_splitters,
+  const uint64_t* h_bucket_offsets,
+  b200rs_stream_t stream)
+{
+  return partition_impl(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items,
+                        key_kind, key_bytes, value_bytes, descending, h_splitters, num_splitters, h_bucket_offsets, 0,
+                        nullptr, nullptr, nullptr, stream);
+}
+
+int b200rs_partition_to_peers(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  const void* d_values_in,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int descending,
+  const uint64_t* h_splitters,
+  int num_splitters,
+  const uint64_t* h_bucket_offsets,
+  int num_dests,
+  const uint64_t* h_segment_ends,
+  const uint64_t* h_rank_dst_keys,
+  const uint64_t* h_rank_dst_vals,
+  b200rs_stream_t stream)
+{
+  if (num_dests < 1)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  return partition_impl(d_temp_storage, temp_storage_bytes, d_keys_in, nullptr, d_values_in, nullptr, num_items, key_kind,
+                        key_bytes, value_bytes, descending, h_splitters, num_splitters, h_bucket_offsets, num_dests,
+                        h_segment_ends, h_rank_dst_keys, h_rank_dst_vals, stream);
 }
 
 int b200rs_timing_enable(int on)

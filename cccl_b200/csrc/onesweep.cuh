@@ -29,6 +29,8 @@
 // coalesced).  Ranks follow (warp, item, lane) == input position order.
 #pragma once
 
+#include <cstddef>
+
 #include "common.cuh"
 
 namespace b200rs
@@ -60,7 +62,8 @@ struct OnesweepSmem
   static constexpr uint32_t OFF_GOFF = OFF_WARP + NW * RADIX * CTR_BYTES; // u64 [256] per-digit output offsets
   static constexpr uint32_t OFF_END  = OFF_GOFF + RADIX * 8;          // u32 [256] end of each digit's staged run
                                                                       // (bucket mode only, else empty)
-  static constexpr uint32_t OFF_MISC = OFF_END + ((OPT & 8) ? RADIX * 4 : 0); // u32 [16]
+  static constexpr uint32_t OFF_PEER = OFF_END + ((OPT & 8) ? RADIX * 4 : 0); // PeerTable copy (bucket mode only)
+  static constexpr uint32_t OFF_MISC = OFF_PEER + ((OPT & 8) ? uint32_t((sizeof(PeerTable) + 15) / 16 * 16) : 0u); // u32 [16]
   static constexpr uint32_t OFF_DATA = OFF_MISC + 64;                 // staged tile (16-byte aligned)
   static constexpr size_t BYTES      = size_t(OFF_DATA) + size_t(TILE) * ITEM_BYTES;
 };
@@ -247,6 +250,25 @@ __device__ __forceinline__ uint32_t tile_digit(const PassArgs& a, U key, int shi
     return id;
   }
   return pass_digit<FLOATK>(key, shift, mask, neg_zero, pos_zero);
+}
+
+// Bucket mode with remote destinations: byte address of the item with partitioned index idx and bucket d.
+// s_peer = shared-window address of the CTA's PeerTable copy.
+__device__ __forceinline__ unsigned long long peer_address(
+  uint32_t s_peer, uint32_t bucket_table_off, uint32_t rank_table_off, uint32_t d, uint32_t idx, uint32_t item_bytes)
+{
+  unsigned long long p = lds64(s_peer + bucket_table_off + d * 8);
+  if (p == 0) // a segment boundary falls inside this bucket (keys tied with a splitter): find the rank by index
+  {
+    const uint32_t nd = lds32(s_peer);
+    uint32_t r        = 0;
+    for (uint32_t j = 0; j + 1 < nd; ++j)
+    {
+      r += idx >= lds32(s_peer + uint32_t(offsetof(PeerTable, seg_end)) + j * 4) ? 1u : 0u;
+    }
+    p = lds64(s_peer + rank_table_off + r * 8);
+  }
+  return p + (unsigned long long) idx * item_bytes;
 }
 
 // warp counters: 32-bit, or 16-bit (OPT_CTR16: two digits per word, so a warp-wide access touches at most four
@@ -621,6 +643,12 @@ __device__ __forceinline__ void onesweep_tile(
         {
           kout[lds64(s_goff + d * 8) + pos] = o;
         }
+        else if (BUCKET && a.peer != nullptr)
+        {
+          *reinterpret_cast<U*>(peer_address(sbase + L::OFF_PEER, uint32_t(offsetof(PeerTable, bucket_dst_keys)),
+                                             uint32_t(offsetof(PeerTable, rank_dst_keys)), d,
+                                             lds32(s_goff + d * 4) + pos, uint32_t(sizeof(U)))) = o;
+        }
         else
         {
           kout[lds32(s_goff + d * 4) + pos] = o;
@@ -670,6 +698,12 @@ __device__ __forceinline__ void onesweep_tile(
         {
           vout[lds64(s_goff + d * 8) + pos] = v;
         }
+        else if (BUCKET && a.peer != nullptr)
+        {
+          *reinterpret_cast<V*>(peer_address(sbase + L::OFF_PEER, uint32_t(offsetof(PeerTable, bucket_dst_vals)),
+                                             uint32_t(offsetof(PeerTable, rank_dst_vals)), d,
+                                             lds32(s_goff + d * 4) + pos, uint32_t(sizeof(V)))) = v;
+        }
         else
         {
           vout[lds32(s_goff + d * 4) + pos] = v;
@@ -714,6 +748,14 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
       sts32(sbase + L::OFF_WARP + (j * NT + tid) * 4, 0);
     }
     static_assert(WORDS % NT == 0, "counter words must divide evenly over the threads");
+  }
+  if ((OPT & OPT_BUCKET) && a.peer != nullptr)
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.peer);
+    for (uint32_t w = tid; w < uint32_t(sizeof(PeerTable) / 4); w += NT)
+    {
+      sts32(sbase + L::OFF_PEER + w * 4, src[w]);
+    }
   }
   __syncthreads();
   const uint32_t tile      = lds32(sbase + L::OFF_MISC + 32);

@@ -218,6 +218,37 @@ class CudaOps:
         _native.check(rc, "b200rs_partition_by_splitters")
         return pk, pv
 
+    def partition_to_peers(self, keys, values, splitters: np.ndarray, sizes: np.ndarray, descending, seg_ends,
+                           dst_keys, dst_vals):
+        """The partition pass fused with the exchange (b200rs_partition_to_peers): segment r of the partitioned order
+        (cut at seg_ends) is stored straight through dst_keys[r] / dst_vals[r] (biased device addresses of rank r's
+        receive buffers).  Returns False when the library has no bucket-mode kernel for these widths."""
+        import ctypes
+
+        import torch
+
+        n = keys.numel()
+        kdt = _torch_np_dtype(keys)
+        vb = values.element_size() if values is not None else 0
+        m, nd = int(splitters.size), len(dst_keys)
+        u64s = lambda xs: (ctypes.c_uint64 * max(len(xs), 1))(*[int(x) & (2**64 - 1) for x in xs])
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+        args = (n, key_kind_of(kdt), kdt.itemsize, vb, int(bool(descending)), u64s(splitters), m, u64s(offs), nd,
+                u64s(seg_ends), u64s(dst_keys), u64s(dst_vals if values is not None else []),
+                torch.cuda.current_stream().cuda_stream)
+        nbytes = ctypes.c_size_t(0)
+        rc = self.lib.b200rs_partition_to_peers(None, ctypes.byref(nbytes), None, None, *args)
+        if rc == 801:  # cudaErrorNotSupported
+            return False
+        _native.check(rc, "b200rs_partition_to_peers (size query)")
+        if n == 0:
+            return True
+        temp = self.scratch("part_temp", nbytes.value, torch.uint8, keys.device)
+        rc = self.lib.b200rs_partition_to_peers(temp.data_ptr(), ctypes.byref(nbytes), keys.data_ptr(),
+                                                values.data_ptr() if values is not None else None, *args)
+        _native.check(rc, "b200rs_partition_to_peers")
+        return True
+
     def partition(self, ids, nbits, keys, values):
         """Stable partition of (keys, values) by the bucket id of each item: one radix pass over the low `nbits` bits
         of the 1-byte ids with the payload as the value (b200rs_sort, pointer form)."""
@@ -410,6 +441,7 @@ class _PeerBuffers:
             self.bufs.append(buf)
             self.hdls.append(hdl)
             self.peers.append([hdl.get_buffer(r, (self.nbytes,), torch.uint8, 0) for r in range(self.world)])
+        self.ptrs = [[int(p) for p in hdl.buffer_ptrs] for hdl in self.hdls]  # [payload][rank] device addresses
 
     @classmethod
     def get(cls, nbytes, device, group, dist):
@@ -470,8 +502,9 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
     """Stable distributed sort of one shard per rank; returns (keys_out, values_out) with len == len(keys).
     The caller's shard is left untouched.  ``stats`` (a dict) receives splitters, exchange counts and, on CUDA, the
     device time of each phase.  ``protocol``: "partition" (histogram select -> one partition pass -> exchange -> one
-    sort) or "sort" (sort -> binary-search select -> exchange -> sort).  ``exchange``: "peer" (NVLink peer copies through
-    symmetric memory), "collective" (all-to-all-v) or "auto" (peer on CUDA + NCCL, else collective).  ``out``: optional
+    sort) or "sort" (sort -> binary-search select -> exchange -> sort).  ``exchange``: "fused" (the partition kernel stores
+    straight into the destination GPUs' receive buffers), "peer" (NVLink peer copies through symmetric memory),
+    "collective" (all-to-all-v) or "auto" (fused, else peer, on CUDA + NCCL; else collective).  ``out``: optional
     (keys_out, values_out) tensors for the result (same length and dtype as the inputs)."""
     import torch
     import torch.distributed as dist
@@ -516,26 +549,54 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
                                                              descending=descending, ops=ops, group=group, dist=dist,
                                                              stats=stats)
         ph.mark("splitters")
-        fused = getattr(ops, "partition_by_splitters", None)
-        part = fused(keys, values, splitters, sizes, descending) if fused is not None else None
-        if part is None:
-            # key / value widths the fused pass is not compiled for: bucket ids + one radix pass over the ids
-            ids = ops.bucket_ids(keys, splitters, descending)
-            part = ops.partition(ids, int(2 * len(splitters)).bit_length(), keys, values)
-        skeys, svals = part
-        if stats is not None:
-            stats["partition_pass"] = "ids" if "ids" in locals() else "fused"
-        ph.mark("partition")
     # boundary matrix with the implicit 0 and n columns: items [edges[i, r], edges[i, r+1]) of source i go to rank r
     edges = np.concatenate([np.zeros((world, 1), dtype=np.int64), bounds, n_all[:, None]], axis=1)
     send = (edges[rank, 1:] - edges[rank, :-1]).tolist()
     recv = (edges[:, rank + 1] - edges[:, rank]).tolist()
     assert sum(recv) == n_local and min(send) >= 0 and min(recv) >= 0
+    use_peer = exchange in ("peer", "fused") or (exchange == "auto" and keys.is_cuda
+                                                 and dist.get_backend(group) == "nccl")
+    peer_done = fused_done = False
+
+    if protocol == "partition":
+        # 2 + 3 fused: ONE kernel partitions by destination and stores every item straight into the receive buffer of
+        # its destination GPU (peer-mapped symmetric memory) -- the compute step and the collective that follows it
+        if use_peer and exchange != "peer" and int(n_all.max()) > 0 and hasattr(ops, "partition_to_peers"):
+            try:
+                es_k = keys.element_size()
+                es_v = values.element_size() if values is not None else 0
+                pb = _PeerBuffers.get(int(n_all.max()) * max(es_k, es_v), keys.device, group, dist)
+                counts = edges[:, 1:] - edges[:, :-1]
+                dst_off = np.cumsum(counts, axis=0) - counts
+                bias = dst_off[rank] - edges[rank, :-1]  # destination index of partitioned index 0, per rank
+                dst_k = [pb.ptrs[0][r] + int(bias[r]) * es_k for r in range(world)]
+                dst_v = [pb.ptrs[1][r] + int(bias[r]) * es_v for r in range(world)]
+                pb.hdls[0].barrier(channel=0)  # every peer has finished reading its receive buffers
+                fused_done = ops.partition_to_peers(keys, values, splitters, sizes, descending,
+                                                    edges[rank, 1:-1].tolist(), dst_k, dst_v)
+                pb.hdls[0].barrier(channel=1)  # every source's stores have landed (needed after the first one, too)
+                if fused_done:
+                    rkeys = pb.bufs[0][: n_local * es_k].view(keys.dtype)
+                    rvals = pb.bufs[1][: n_local * es_v].view(values.dtype) if values is not None else None
+                    peer_done = True
+                    ph.mark("partition")
+            except (RuntimeError, ImportError, AttributeError) as ex:  # symmetric memory not available
+                if exchange == "fused":
+                    raise
+                if stats is not None:
+                    stats["peer_exchange_unavailable"] = repr(ex)
+        if not fused_done:
+            fused = getattr(ops, "partition_by_splitters", None)
+            part = fused(keys, values, splitters, sizes, descending) if fused is not None else None
+            if part is None:
+                # key / value widths the fused pass is not compiled for: bucket ids + one radix pass over the ids
+                ids = ops.bucket_ids(keys, splitters, descending)
+                part = ops.partition(ids, int(2 * len(splitters)).bit_length(), keys, values)
+            skeys, svals = part
+            ph.mark("partition")
 
     # 3. exchange, receive buffer in source-rank order
-    use_peer = exchange == "peer" or (exchange == "auto" and keys.is_cuda and dist.get_backend(group) == "nccl")
-    peer_done = False
-    if use_peer and int(n_all.max()) > 0:
+    if not fused_done and use_peer and int(n_all.max()) > 0:
         try:
             rkeys, rvals = _peer_exchange(dist, group, rank, edges, [skeys, svals], n_local, int(n_all.max()))
             peer_done = True
@@ -561,10 +622,10 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
     ph.mark("final_sort")
     if stats is not None:
         stats["protocol"] = protocol
-        stats["exchange"] = "peer" if peer_done else "collective"
+        stats["exchange"] = "fused" if fused_done else ("peer" if peer_done else "collective")
         stats["send_counts"] = send
         stats["recv_counts"] = recv
-        item = key_bytes + (svals.element_size() if svals is not None else 0)
+        item = key_bytes + (values.element_size() if values is not None else 0)
         stats["exchange_bytes_out"] = (n_local - send[rank]) * item
         stats["exchange_bytes_in"] = (n_local - recv[rank]) * item
         stats["phase_ms"] = ph.result()

@@ -239,6 +239,34 @@ B200RS_API int b200rs_partition_by_splitters(
   const uint64_t* h_bucket_offsets,
   b200rs_stream_t stream);
 
+/*
+ * The partition pass FUSED with the exchange: the same launch as b200rs_partition_by_splitters, but the partitioned
+ * order is cut into num_dests contiguous segments (h_segment_ends[r] = first partitioned index that does not go to
+ * ranks <= r; num_dests - 1 entries) and segment r is stored straight into rank r's receive buffer over NVLink.
+ * h_rank_dst_keys[r] / h_rank_dst_vals[r] (HOST arrays of device addresses valid on THIS GPU, e.g. peer-mapped
+ * symmetric memory) are biased: the item with partitioned index idx is stored at address + idx * item size.
+ * The caller orders the launch between two cross-GPU barriers (receive buffers free / all stores landed).
+ * One kernel does the compute step and the collective that follows it (SURVEY.md 8e steps 3 + 5).
+ */
+B200RS_API int b200rs_partition_to_peers(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  const void* d_values_in,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int descending,
+  const uint64_t* h_splitters,
+  int num_splitters,
+  const uint64_t* h_bucket_offsets,
+  int num_dests,
+  const uint64_t* h_segment_ends,
+  const uint64_t* h_rank_dst_keys,
+  const uint64_t* h_rank_dst_vals,
+  b200rs_stream_t stream);
+
 /* Number of kernel launches / async ops the last b200rs_sort call on this host thread enqueued
  * (bench.py's `gpu_launches`).  Thread-local. */
 B200RS_API int b200rs_last_launch_count(void);

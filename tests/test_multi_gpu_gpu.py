@@ -72,8 +72,12 @@ def _worker(rank, world, port, backend, results, protocol="partition", exchange=
         stats = {}
         ok, ov = distributed_sort(d_k, d_v, descending=desc, stats=stats, protocol=protocol, exchange=exchange)
         torch.cuda.synchronize()
-        if backend == "nccl" and exchange in ("auto", "peer") and stats.get("exchange") != "peer" and sum(ns) > 0:
-            failures.append((name, "peer exchange not used: " + str(stats.get("peer_exchange_unavailable"))))
+        if backend == "nccl" and sum(ns) > 0 and protocol == "partition":
+            want = {"auto": ("fused" if np.dtype(dtype).itemsize >= 4 else "peer"), "peer": "peer",
+                    "collective": "collective"}[exchange]
+            if stats.get("exchange") != want:
+                failures.append((name, f"exchange {stats.get('exchange')} != {want}: "
+                                       + str(stats.get("peer_exchange_unavailable"))))
         if not np.array_equal(_host(d_k).view(np.uint8), shards[rank].view(np.uint8)):
             failures.append((name, "input shard modified"))
         allk, allv = np.concatenate(shards), np.concatenate(vshards)
@@ -112,6 +116,7 @@ def test_distributed_sort_cuda_ranks_sharing_one_gpu(world, protocol):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("protocol,exchange", [("partition", "auto"), ("partition", "collective"), ("sort", "collective")])
+@pytest.mark.parametrize("protocol,exchange", [("partition", "auto"), ("partition", "peer"), ("partition", "collective"),
+                                               ("sort", "collective")])
 def test_distributed_sort_nccl(protocol, exchange):
     _run(min(torch.cuda.device_count(), 3), "nccl", protocol, exchange)
