@@ -9,6 +9,7 @@ if [ "$2" != "skip-tests" ]; then
   timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
   tail -5 $OUT/pytest_gpu.log
 fi
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $OUT/smoke.log 2>&1; tail -1 $OUT/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; tail -c 3000 $OUT/bench.json
 for W in "sortpairs_u64_u32_2^28_uniform" "sortpairs_u64_u32_2^28_entropy0.201" "sortkeys_f32_desc_2^28_bits8_24" "sortkeys_f32_desc_2^28" "sortkeys_i64_desc_2^28_bits16_48" "sortkeys_i64_desc_2^28" "sortpairs_u32_u32_2^28_uniform" "sortkeys_u32_2^28_entropy0.201" "sortkeys_u32_2^28_equal" "sortkeys_u32_2^28_few16" "sortkeys_u32_2^28_sorted"; do
   timeout 300 python bench.py --workload "$W" --steps 10 --warmup 3 --no-cpu-baseline >> $OUT/bench_other.jsonl 2>> $OUT/bench.err
