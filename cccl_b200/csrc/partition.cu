@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
   __shared__ unsigned int sh[MAX_SPLITTERS * RADIX];
   __shared__ unsigned long long s_prefix[MAX_SPLITTERS + 1];
   __shared__ int s_first[MAX_SPLITTERS + 1];
-  __shared__ unsigned int s_bitmap[8]; // round 1: which top bytes are prefixes
+  __shared__ signed char s_row[RADIX]; // round 1 (one-byte prefixes): histogram row of a top byte, or -1
   __shared__ unsigned int s_emitted;
   const unsigned long long slice_cap = (cand_capacity / gridDim.x) & ~15ull; // slices stay 16-byte aligned
   if (threadIdx.x == 0)
@@ -58,9 +58,9 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
     s_emitted = 0;
   }
   const bool one_byte_prefix = hi_shift == int(sizeof(U) * 8) - RADIX_BITS;
-  if (threadIdx.x < 8)
+  if (threadIdx.x < RADIX)
   {
-    s_bitmap[threadIdx.x] = 0;
+    s_row[threadIdx.x] = -1;
   }
   for (int i = threadIdx.x; i < np * RADIX; i += PART_THREADS)
   {
@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
     }
     s_prefix[threadIdx.x] = pf;
     s_first[threadIdx.x]  = first;
-    if (one_byte_prefix)
+    if (one_byte_prefix && first == int(threadIdx.x))
     {
-      atomicOr(&s_bitmap[(pf >> 5) & 7], 1u << (pf & 31));
+      s_row[pf & (RADIX - 1)] = (signed char) threadIdx.x;
     }
   }
   __syncthreads();
@@ -133,33 +133,50 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
         // hi_shift == key bits on the first round: every key carries the (empty) prefix
         const unsigned long long hi = hi_shift >= int(sizeof(U) * 8) ? 0ull : (unsigned long long) (v >> hi_shift);
         const unsigned int bin      = (unsigned int) (v >> lo_shift) & (RADIX - 1);
-        bool maybe                  = i < n;
+        int row = -1;
         if (one_byte_prefix)
         {
-          maybe = maybe && ((s_bitmap[(hi >> 5) & 7] >> (hi & 31)) & 1u) != 0;
-        }
-        if (!__any_sync(0xffffffffu, maybe))
-        {
-          continue; // the usual case in a full scan: nobody in the warp carries a prefix
-        }
-        int row = -1;
-        if (maybe)
-        {
-          for (int p = 0; p < np; ++p)
+          // one table look-up instead of a loop over the prefixes: this is the only round that scans every key
+          row = i < n ? int(s_row[hi & (RADIX - 1)]) : -1;
+          if (!__any_sync(0xffffffffu, row >= 0))
           {
-            row = (hi == s_prefix[p] && s_first[p] == p) ? p : row;
+            continue;
+          }
+        }
+        else
+        {
+          const bool maybe = i < n;
+          if (!__any_sync(0xffffffffu, maybe))
+          {
+            continue;
+          }
+          if (maybe)
+          {
+            for (int p = 0; p < np; ++p)
+            {
+              row = (hi == s_prefix[p] && s_first[p] == p) ? p : row;
+            }
           }
         }
         const bool hit        = row >= 0;
         const unsigned int hm = __ballot_sync(0xffffffffu, hit);
         if (hit)
         {
-          // warp-aggregated: one shared atomic per distinct (row, bin), so all-equal keys do not serialise
-          const unsigned int slot  = (unsigned int) row * RADIX + bin;
-          const unsigned int peers = __match_any_sync(hm, slot);
-          if ((peers & ((1u << lane) - 1u)) == 0)
+          const unsigned int slot = (unsigned int) row * RADIX + bin;
+          if (__popc(hm) >= 8)
           {
-            atomicAdd(&sh[slot], (unsigned int) __popc(peers));
+            // many hits in one warp means duplicated keys: aggregate, one shared atomic per distinct (row, bin), so
+            // all-equal keys do not serialise (MATCH.ANY itself is slow -- about one per 40 cycles per SM -- which is
+            // why the common case of a few scattered hits below does not use it)
+            const unsigned int peers = __match_any_sync(hm, slot);
+            if ((peers & ((1u << lane) - 1u)) == 0)
+            {
+              atomicAdd(&sh[slot], (unsigned int) __popc(peers));
+            }
+          }
+          else
+          {
+            atomicAdd(&sh[slot], 1u);
           }
         }
         if (my_out != nullptr && hm != 0)
