@@ -383,3 +383,51 @@ def test_full_size_properties(case):
         for s in range(0, n, chunk):
             idx = vout[s:s + chunk].to(torch.int64)
             assert bool((keys.view(torch.int64)[idx] == out.view(torch.int64)[s:s + chunk]).all())
+
+
+@pytest.mark.parametrize("kb,extra", [(1, 12_345), (2, 4_099)])
+def test_more_than_2_to_the_32_items(kb, extra):
+    """NumItemsT = 64-bit (reference: choose_offset.cuh:35-52, large-N tests catch2_test_device_radix_sort_keys.cu:488-519):
+    N > 2^32 items takes the 64-bit-offset kernels and several chained portions per pass for real (not through the
+    diagnostic switches).  1- and 2-byte keys keep it to one or two passes; the check is exact and runs on the device:
+    the output of a key sort is the digit histogram written out in order."""
+    from cccl_b200 import _native
+
+    n = (1 << 32) + extra
+    free, _ = torch.cuda.mem_get_info()
+    if free < 3 * n * kb + (4 << 30):
+        pytest.skip("not enough free device memory")
+    g = torch.Generator(device="cuda").manual_seed(17)
+    words = (n * kb + 7) // 8
+    keys = torch.randint(-(2**63), 2**63 - 1, (words,), dtype=torch.int64, device="cuda", generator=g).view(torch.uint8)[: n * kb]
+    out = torch.empty_like(keys)
+    need, _ = _native.sort_raw(0, 0, keys.data_ptr(), out.data_ptr(), 0, 0, n, 0, kb, 0, 0, 8 * kb, True, False)
+    temp = torch.empty(need, dtype=torch.uint8, device="cuda")
+    _, sel = _native.sort_raw(temp.data_ptr(), need, keys.data_ptr(), out.data_ptr(), 0, 0, n, 0, kb, 0, 0, 8 * kb, True,
+                              False)
+    torch.cuda.synchronize()
+    assert sel == 1
+    launches = _native.lib().b200rs_last_launch_count()
+    assert launches >= 3 + kb * 5, launches  # 5 portions of < 2^30 items per pass
+    del temp
+    dt = torch.uint8 if kb == 1 else torch.int16
+    kin, kout = keys.view(dt), out.view(dt)
+    nbins = 1 << (8 * kb)
+    counts = torch.zeros(nbins, dtype=torch.int64, device="cuda")
+    chunk = 1 << 28
+    for lo in range(0, n, chunk):  # histogram of the input in pieces (bincount wants int64 copies)
+        piece = kin[lo:lo + chunk].to(torch.int64) & (nbins - 1)
+        counts += torch.bincount(piece, minlength=nbins)
+    assert int(counts.sum()) == n
+    # descending: bin nbins-1 first.  Compare run boundaries instead of materialising the expected array.
+    order = torch.arange(nbins - 1, -1, -1, device="cuda")
+    ends = torch.cumsum(counts[order], 0)
+    starts = ends - counts[order]
+    nz = counts[order] > 0
+    first = (kout[starts[nz].clamp(max=n - 1)].to(torch.int64) & (nbins - 1))
+    last = (kout[(ends[nz] - 1)].to(torch.int64) & (nbins - 1))
+    assert torch.equal(first, order[nz]) and torch.equal(last, order[nz])
+    # and every adjacent pair is non-increasing
+    for lo in range(0, n - 1, chunk):
+        a = kout[lo:lo + chunk + 1].to(torch.int32) & (nbins - 1)
+        assert bool((a[1:] <= a[:-1]).all())
