@@ -338,12 +338,65 @@ void edge_cases()
   check_keys<uint32_t>(10000, true, 7, 7, true, nullptr);
 }
 
+// 16-bit floating-point keys through the shim (reference: device_radix_sort.cuh:51-57, util_type.cuh:1017-1095):
+// compared with a host stable sort on the float values; -0.0 / +0.0 tie and keep input order.
+template <class H>
+void half_keys(size_t n, bool descending)
+{
+  std::vector<H> keys(n);
+  std::vector<uint32_t> vals(n);
+  std::mt19937 rng(77);
+  for (size_t i = 0; i < n; ++i)
+  {
+    const float f = float(int(rng() % 4001) - 2000) / 16.0f; // exactly representable in half and bfloat16
+    keys[i]       = H(i % 13 == 0 ? -0.0f : (i % 17 == 0 ? 0.0f : f));
+    vals[i]       = uint32_t(i);
+  }
+  dev<H> ki(keys), ko(n);
+  dev<uint32_t> vi(vals), vo(n);
+  size_t bytes = 0;
+  auto e = descending ? cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, ki.p, ko.p, vi.p, vo.p, n)
+                      : cub::DeviceRadixSort::SortPairs(nullptr, bytes, ki.p, ko.p, vi.p, vo.p, n);
+  REQUIRE(e == cudaSuccess);
+  void* tmp;
+  cudaMalloc(&tmp, bytes);
+  e = descending ? cub::DeviceRadixSort::SortPairsDescending(tmp, bytes, ki.p, ko.p, vi.p, vo.p, n)
+                 : cub::DeviceRadixSort::SortPairs(tmp, bytes, ki.p, ko.p, vi.p, vo.p, n);
+  cudaDeviceSynchronize();
+  REQUIRE(e == cudaSuccess);
+  cudaFree(tmp);
+  std::vector<uint32_t> order(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    order[i] = uint32_t(i);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    const float fa = float(keys[a]), fb = float(keys[b]);
+    return descending ? fa > fb : fa < fb;
+  });
+  REQUIRE(vo.host() == order);
+  const auto got = ko.host();
+  bool same      = true;
+  for (size_t i = 0; i < n; ++i)
+  {
+    same = same && memcmp(&got[i], &keys[order[i]], sizeof(H)) == 0;
+  }
+  REQUIRE(same);
+}
+
 int main()
 {
   cudaStream_t stream;
   cudaStreamCreate(&stream);
   env_api_goldens();
   edge_cases();
+  for (size_t n : {size_t(1000), size_t(300007)})
+  {
+    half_keys<__half>(n, false);
+    half_keys<__half>(n, true);
+    half_keys<__nv_bfloat16>(n, false);
+    half_keys<__nv_bfloat16>(n, true);
+  }
   const size_t sizes[] = {1, 2, 255, 4864, 4865, 100000, (1u << 21) + 17};
   for (size_t n : sizes)
   {
