@@ -73,6 +73,7 @@ class CudaOps:
     def __init__(self):
         self.lib = _native.lib()  # raises if the CUDA library is absent: there is no CPU path
         self._scratch = {}
+        self.kernel_launches = 0  # kernels of libb200rs.so launched through this object (bench.py's gpu_launches)
 
     def scratch(self, name, numel, dtype, device):
         """Grow-only scratch tensor kept across calls (stream-ordered reuse: one stream per CudaOps object).  Scratch
@@ -103,12 +104,19 @@ class CudaOps:
             kw = dict(d_in_keys=keys, d_out_keys=okeys, d_in_values=values, d_out_values=ovals, num_items=n)
             nbytes = sorter(temp_storage=None, **kw)
             sorter(temp_storage=self.scratch("sort_temp", nbytes, torch.uint8, keys.device), **kw)
+            self.kernel_launches += self._sort_kernels()
             return okeys, ovals
         kb = DoubleBuffer(keys, torch.empty_like(keys))
         vb = DoubleBuffer(values, torch.empty_like(values)) if values is not None else None
         keep = radix_sort(d_in_keys=kb, d_out_keys=None, d_in_values=vb, d_out_values=None, num_items=n, order=order)
         del keep  # stream-ordered: the caching allocator reuses it only for later work on the same stream
+        self.kernel_launches += self._sort_kernels()
         return kb.current(), (vb.current() if vb is not None else None)
+
+    def _sort_kernels(self):
+        # stream ops of the last b200rs_sort call minus its one memset (single-tile sorts have none)
+        n = self.lib.b200rs_last_launch_count()
+        return n - 1 if n > 1 else n
 
     def splitter_ranks(self, sorted_keys, probes_bits: np.ndarray, descending):
         """probes_bits: uint64 numpy array of user-domain key bit patterns.  Returns (lt, eq) int64 CUDA tensors."""
@@ -139,6 +147,7 @@ class CudaOps:
             keys.data_ptr() if keys.numel() else 0, keys.numel(), key_kind_of(kdt), kdt.itemsize, bits - RADIX_BITS,
             bits, int(bool(descending)), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
         _native.check(rc, "b200rs_digit_histogram")
+        self.kernel_launches += 1
         return out.view(1, RADIX)
 
     def select_histogram(self, keys, prefixes, rnd: int, descending, candidates="none"):
@@ -166,6 +175,7 @@ class CudaOps:
             prefixes.data_ptr(), m, rnd, out.data_ptr(), cin or None, cst_in or None, cout or None, cst_out or None,
             cap, torch.cuda.current_stream().cuda_stream)
         _native.check(rc, "b200rs_select_histogram")
+        self.kernel_launches += 1
         return out
 
     def bucket_ids(self, keys, splitters: np.ndarray, descending):
@@ -183,6 +193,7 @@ class CudaOps:
             int(bool(descending)), arr, m, ids.data_ptr() if keys.numel() else 0,
             torch.cuda.current_stream().cuda_stream)
         _native.check(rc, "b200rs_bucket_ids")
+        self.kernel_launches += 1
         return ids
 
     def partition_by_splitters(self, keys, values, splitters: np.ndarray, sizes: np.ndarray, descending):
@@ -216,6 +227,7 @@ class CudaOps:
             temp.data_ptr(), ctypes.byref(nbytes), keys.data_ptr(), pk.data_ptr(),
             values.data_ptr() if values is not None else None, pv.data_ptr() if pv is not None else None, *args)
         _native.check(rc, "b200rs_partition_by_splitters")
+        self.kernel_launches += 1
         return pk, pv
 
     def partition_to_peers(self, keys, values, splitters: np.ndarray, sizes: np.ndarray, descending, seg_ends,
@@ -247,6 +259,7 @@ class CudaOps:
         rc = self.lib.b200rs_partition_to_peers(temp.data_ptr(), ctypes.byref(nbytes), keys.data_ptr(),
                                                 values.data_ptr() if values is not None else None, *args)
         _native.check(rc, "b200rs_partition_to_peers")
+        self.kernel_launches += 1
         return True
 
     def partition(self, ids, nbits, keys, values):
@@ -622,6 +635,7 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
     ph.mark("final_sort")
     if stats is not None:
         stats["protocol"] = protocol
+        stats["kernel_launches_total"] = getattr(ops, "kernel_launches", None)
         stats["exchange"] = "fused" if fused_done else ("peer" if peer_done else "collective")
         stats["send_counts"] = send
         stats["recv_counts"] = recv

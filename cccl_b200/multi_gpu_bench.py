@@ -44,7 +44,12 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
     for _ in range(args.warmup):
         distributed_sort(keys, vals, stats=stats, out=out_buf)
     barrier()
-    launches = lib.b200rs_last_launch_count() * 2  # two local sorts per step (+ the splitter probes)
+    from .multi_gpu import _default_ops
+
+    before = _default_ops().kernel_launches
+    distributed_sort(keys, vals, out=out_buf)
+    launches = _default_ops().kernel_launches - before  # kernels of libb200rs.so per step on this GPU
+    barrier()
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase = {}
