@@ -11,7 +11,8 @@ using K = uint64_t;
 #define T(VB, NT, IPT, MINB, LBW) make_tma_config<K, VB, NT, IPT, MINB, LBW>()
 
 static const OnesweepConfig cfg_v0[] = {
-  OB(0, 256, 24, 3, 7),
+  OB(0, 256, 20, 4, 7),
+  O(0, 256, 24, 3, 7),
   C(0, 256, 24, 3),
   O(0, 256, 32, 2, 7),
   T(0, 256, 24, 3, 4)
