@@ -288,7 +288,8 @@ class CudaOps:
 
 
 # ----------------------------------------------------------------------------------------------- splitter selection
-def select_splitters_unsorted(keys, targets, *, kind, key_bytes, descending, ops, group, dist, stats=None):
+def select_splitters_unsorted(keys, targets, *, kind, key_bytes, descending, ops, group, dist, stats=None,
+                              top_hist=None):
     """Exact splitters from the UNSORTED shard.  For every global target rank t finds the bit-ordered value x of the
     t-th smallest key of the whole job by MSD radix select, and returns (bounds, splitters, sizes): bounds[(world, nt)]
     = number of items of each source rank that go to ranks <= the target's, counted in the order "bucket id, then local
@@ -309,7 +310,8 @@ def select_splitters_unsorted(keys, targets, *, kind, key_bytes, descending, ops
     eq_local = torch.zeros(nt, dtype=torch.int64, device=dev)
     for rnd in range(key_bytes):
         if rnd == 0:
-            h_local = ops.top_digit_histogram(keys, descending).expand(nt, RADIX)
+            h0 = top_hist if top_hist is not None else ops.top_digit_histogram(keys, descending)
+            h_local = h0.expand(nt, RADIX)
         else:
             # the first full scan compacts the keys that can still matter; later rounds only look at those
             mode = "none" if key_bytes <= 2 else ("emit" if rnd == 1 else "use")
@@ -540,6 +542,8 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
             stats["phase_ms"] = ph.result()
         return res
 
+    # the first select round only needs the shard: start it before the host waits for the other ranks' sizes
+    top_hist = ops.top_digit_histogram(keys, descending) if protocol == "partition" else None
     # rank r must end with the global stable positions [sum(n[:r]), sum(n[:r+1]))
     counts = torch.tensor([n_local], dtype=torch.int64, device=keys.device)
     allcounts = [torch.empty_like(counts) for _ in range(world)]
@@ -560,7 +564,7 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
             raise ValueError("the partition protocol supports up to 16 ranks (one box)")
         bounds, splitters, sizes = select_splitters_unsorted(keys, targets, kind=kind, key_bytes=key_bytes,
                                                              descending=descending, ops=ops, group=group, dist=dist,
-                                                             stats=stats)
+                                                             stats=stats, top_hist=top_hist)
         ph.mark("splitters")
     # boundary matrix with the implicit 0 and n columns: items [edges[i, r], edges[i, r+1]) of source i go to rank r
     edges = np.concatenate([np.zeros((world, 1), dtype=np.int64), bounds, n_all[:, None]], axis=1)
