@@ -8,10 +8,14 @@
 //
 // usage: ref_cub_radix_sort sort  <ktype> <vbytes> <n> <desc> <begin_bit> <end_bit> <keys.bin> <vals.bin|-> <out_keys.bin> <out_vals.bin|->
 //        ref_cub_radix_sort bench <ktype> <vbytes> <log2n> <desc> <begin_bit> <end_bit> <and_rounds> <iters>
+//        ref_cub_radix_sort segsort <ktype> <vbytes> <n> <desc> <begin_bit> <end_bit> <keys.bin> <vals.bin|-> <out_keys.bin> <out_vals.bin|-> <num_segments> <begin_offsets.bin> <end_offsets.bin>
+//          (cub::DeviceSegmentedRadixSort; offsets are int64; the output buffers are pre-filled with the input so that
+//           positions outside every segment are defined)
 //   ktype in {u8,i8,u16,i16,f16,bf16,u32,i32,f32,u64,i64,f64}; vbytes in {0,4,8}
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <cstdint>
 #include <cstdio>
@@ -45,6 +49,20 @@ cudaError_t do_sort(void* tmp, size_t& bytes, const K* kin, K* kout, const V* vi
               : cub::DeviceRadixSort::SortKeys(tmp, bytes, kin, kout, n, b, e);
 }
 
+template <class K, class V>
+cudaError_t do_segsort(void* tmp, size_t& bytes, const K* kin, K* kout, const V* vin, V* vout, long long n, long long segs,
+                       const long long* bo, const long long* eo, bool desc, int b, int e, bool pairs)
+{
+  using S = cub::DeviceSegmentedRadixSort;
+  if (pairs)
+  {
+    return desc ? S::SortPairsDescending(tmp, bytes, kin, kout, vin, vout, n, segs, bo, eo, b, e)
+                : S::SortPairs(tmp, bytes, kin, kout, vin, vout, n, segs, bo, eo, b, e);
+  }
+  return desc ? S::SortKeysDescending(tmp, bytes, kin, kout, n, segs, bo, eo, b, e)
+              : S::SortKeys(tmp, bytes, kin, kout, n, segs, bo, eo, b, e);
+}
+
 static std::vector<char> slurp(const char* path, size_t bytes)
 {
   std::vector<char> buf(bytes);
@@ -67,6 +85,58 @@ static void dump(const char* path, const void* p, size_t bytes)
     exit(3);
   }
   fclose(f);
+}
+
+// cub::DeviceSegmentedRadixSort on files (instantiated for a few key types only: it is a checker for the segmented
+// oracle, SURVEY.md 8f-1, not a benchmark)
+template <class K, class V>
+int run_seg(int argc, char** argv, bool pairs)
+{
+  (void) argc;
+  const bool desc = atoi(argv[5]) != 0;
+  const int b = atoi(argv[6]), e = atoi(argv[7]);
+  {
+    const size_t n    = strtoull(argv[4], nullptr, 10);
+    const size_t segs = strtoull(argv[12], nullptr, 10);
+    K *kin, *kout;
+    V *vin = nullptr, *vout = nullptr;
+    long long *bo, *eo;
+    CK(cudaMalloc(&kin, n * sizeof(K) + 16));
+    CK(cudaMalloc(&kout, n * sizeof(K) + 16));
+    CK(cudaMalloc(&bo, segs * 8 + 16));
+    CK(cudaMalloc(&eo, segs * 8 + 16));
+    auto hk = slurp(argv[8], n * sizeof(K));
+    auto hb = slurp(argv[13], segs * 8);
+    auto he = slurp(argv[14], segs * 8);
+    CK(cudaMemcpy(kin, hk.data(), n * sizeof(K), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(kout, hk.data(), n * sizeof(K), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(bo, hb.data(), segs * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(eo, he.data(), segs * 8, cudaMemcpyHostToDevice));
+    if (pairs)
+    {
+      CK(cudaMalloc(&vin, n * sizeof(V) + 16));
+      CK(cudaMalloc(&vout, n * sizeof(V) + 16));
+      auto hv = slurp(argv[9], n * sizeof(V));
+      CK(cudaMemcpy(vin, hv.data(), n * sizeof(V), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(vout, hv.data(), n * sizeof(V), cudaMemcpyHostToDevice));
+    }
+    size_t bytes = 0;
+    CK((do_segsort<K, V>(nullptr, bytes, kin, kout, vin, vout, (long long) n, (long long) segs, bo, eo, desc, b, e, pairs)));
+    void* tmp;
+    CK(cudaMalloc(&tmp, bytes + 16));
+    CK((do_segsort<K, V>(tmp, bytes, kin, kout, vin, vout, (long long) n, (long long) segs, bo, eo, desc, b, e, pairs)));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(hk.data(), kout, n * sizeof(K), cudaMemcpyDeviceToHost));
+    dump(argv[10], hk.data(), n * sizeof(K));
+    if (pairs)
+    {
+      std::vector<char> hv(n * sizeof(V));
+      CK(cudaMemcpy(hv.data(), vout, n * sizeof(V), cudaMemcpyDeviceToHost));
+      dump(argv[11], hv.data(), n * sizeof(V));
+    }
+    return 0;
+  }
+  return 1;
 }
 
 template <class K, class V>
@@ -191,6 +261,21 @@ int main(int argc, char** argv)
     return 1;
   }
   const std::string kt = argv[2];
+  if (std::string(argv[1]) == "segsort")
+  {
+    if (argc < 15)
+    {
+      fprintf(stderr, "segsort needs 14 arguments\n");
+      return 1;
+    }
+    const bool pairs = atoi(argv[3]) == 4;
+    if (kt == "u32") return run_seg<uint32_t, uint32_t>(argc, argv, pairs);
+    if (kt == "f32") return run_seg<float, uint32_t>(argc, argv, pairs);
+    if (kt == "u64") return run_seg<uint64_t, uint32_t>(argc, argv, pairs);
+    if (kt == "i64") return run_seg<int64_t, uint32_t>(argc, argv, pairs);
+    fprintf(stderr, "segsort: ktype in {u32,f32,u64,i64}, vbytes in {0,4}\n");
+    return 1;
+  }
   if (kt == "u8") return by_value<uint8_t>(argc, argv);
   if (kt == "i8") return by_value<int8_t>(argc, argv);
   if (kt == "u16") return by_value<uint16_t>(argc, argv);

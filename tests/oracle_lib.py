@@ -119,3 +119,22 @@ def ref_thrust_sort(keys: np.ndarray, values: np.ndarray | None = None, *, desce
                                v.dtype.itemsize if v is not None else 0, int(descending))
     assert secs >= 0, "unsupported type combination in the reference wrapper"
     return (k, v, secs) if v is not None else (k, secs)
+
+
+def oracle_segmented_sort(keys: np.ndarray, values, begin_offsets, end_offsets, *, descending=False, begin_bit=0,
+                          end_bit=None):
+    """CPU restatement of the segmented reference check (cub/test/catch2_radix_sort_helper.cuh:314-429,
+    cub/cub/device/device_segmented_radix_sort.cuh): every segment [begin[s], end[s]) is sorted independently with the
+    same stable, bit-window-aware order as oracle_sort; positions outside every segment keep the input.
+    Groundwork for SURVEY.md 8f-1 (cub::DeviceSegmentedRadixSort); pinned by tests/golden/cubseg_*.npz."""
+    kout = np.array(keys, copy=True)
+    vout = np.array(values, copy=True) if values is not None else None
+    for b, e in zip(np.asarray(begin_offsets).tolist(), np.asarray(end_offsets).tolist()):
+        if e <= b:
+            continue
+        if values is None:
+            kout[b:e] = oracle_sort(keys[b:e], descending=descending, begin_bit=begin_bit, end_bit=end_bit)
+        else:
+            kout[b:e], vout[b:e] = oracle_sort(keys[b:e], values[b:e], descending=descending, begin_bit=begin_bit,
+                                               end_bit=end_bit)
+    return (kout, vout) if values is not None else kout

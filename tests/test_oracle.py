@@ -120,3 +120,24 @@ def test_16_bit_float_keys_in_the_oracle():
     bits = np.array([0x7E00, 0xFE00, 0x3C00, 0xBC00, 0x7C00, 0xFC00], dtype=np.uint16).view(np.float16)
     ok = oracle_sort(bits)
     assert ok.view(np.uint16).tolist() == [0xFE00, 0xFC00, 0xBC00, 0x3C00, 0x7C00, 0x7E00]  # -NaN -inf -1 1 +inf +NaN
+
+
+def test_segmented_oracle_against_reference_cub_fixtures():
+    """oracle_segmented_sort (the checker for SURVEY.md 8f-1) against outputs of the UNMODIFIED reference's
+    cub::DeviceSegmentedRadixSort run on a B200 (tests/golden/make_golden_cub_segmented.py): empty segments, gaps,
+    one-item segments, a segment above the single-tile size, descending, bit window, +-0.0."""
+    import glob
+
+    from oracle_lib import oracle_segmented_sort
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cubseg_*.npz")))
+    assert len(files) >= 5
+    for f in files:
+        z = np.load(f)
+        kw = dict(descending=bool(z["descending"]), begin_bit=int(z["begin_bit"]), end_bit=int(z["end_bit"]))
+        if "vals_in" in z.files:
+            ok, ov = oracle_segmented_sort(z["keys_in"], z["vals_in"], z["begin_offsets"], z["end_offsets"], **kw)
+            assert np.array_equal(ov, z["vals_out"]), f
+        else:
+            ok = oracle_segmented_sort(z["keys_in"], None, z["begin_offsets"], z["end_offsets"], **kw)
+        assert np.array_equal(ok.view(np.uint8), z["keys_out"].view(np.uint8)), f
