@@ -1,7 +1,7 @@
-"""Generates tests/golden/cubseg_*.npz from the UNMODIFIED reference's cub::DeviceSegmentedRadixSort (3.6.0, compiled
+"""Generates tests/golden/segmented/cubseg_*.npz from the UNMODIFIED reference's cub::DeviceSegmentedRadixSort (3.6.0, compiled
 from /root/reference into oracle/_ref/ref_cub_radix_sort, mode `segsort`).  Must run on a GPU box:
 
-    gpurun -- python tests/golden/make_golden_cub_segmented.py gpurun_out/golden_cubseg   # then copy the .npz files here
+    gpurun -- python tests/golden/segmented/make_golden_cub_segmented.py gpurun_out/golden_cubseg   # then copy the .npz files here
 
 They pin tests/oracle_lib.py:oracle_segmented_sort -- the checker for SURVEY.md 8f-1, the next row of the scope table --
 including empty segments, gaps between segments, segments of one item, a segment larger than the reference's
@@ -14,7 +14,7 @@ import tempfile
 
 import numpy as np
 
-HERE = os.path.dirname(os.path.abspath(__file__))
+HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/golden
 sys.path.insert(0, os.path.dirname(HERE))
 from gen import make_keys, make_values  # noqa: E402
 
@@ -80,4 +80,4 @@ def main(outdir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "."))
+    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "segmented"))

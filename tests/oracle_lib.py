@@ -126,7 +126,7 @@ def oracle_segmented_sort(keys: np.ndarray, values, begin_offsets, end_offsets, 
     """CPU restatement of the segmented reference check (cub/test/catch2_radix_sort_helper.cuh:314-429,
     cub/cub/device/device_segmented_radix_sort.cuh): every segment [begin[s], end[s]) is sorted independently with the
     same stable, bit-window-aware order as oracle_sort; positions outside every segment keep the input.
-    Groundwork for SURVEY.md 8f-1 (cub::DeviceSegmentedRadixSort); pinned by tests/golden/cubseg_*.npz."""
+    Groundwork for SURVEY.md 8f-1 (cub::DeviceSegmentedRadixSort); pinned by tests/golden/segmented/cubseg_*.npz."""
     kout = np.array(keys, copy=True)
     vout = np.array(values, copy=True) if values is not None else None
     for b, e in zip(np.asarray(begin_offsets).tolist(), np.asarray(end_offsets).tolist()):

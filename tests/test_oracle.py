@@ -124,13 +124,13 @@ def test_16_bit_float_keys_in_the_oracle():
 
 def test_segmented_oracle_against_reference_cub_fixtures():
     """oracle_segmented_sort (the checker for SURVEY.md 8f-1) against outputs of the UNMODIFIED reference's
-    cub::DeviceSegmentedRadixSort run on a B200 (tests/golden/make_golden_cub_segmented.py): empty segments, gaps,
+    cub::DeviceSegmentedRadixSort run on a B200 (tests/golden/segmented/make_golden_cub_segmented.py): empty segments, gaps,
     one-item segments, a segment above the single-tile size, descending, bit window, +-0.0."""
     import glob
 
     from oracle_lib import oracle_segmented_sort
 
-    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cubseg_*.npz")))
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "segmented", "cubseg_*.npz")))
     assert len(files) >= 5
     for f in files:
         z = np.load(f)
