@@ -19,3 +19,15 @@ def _built():
     import __graft_entry__ as g
 
     g.build(quiet=True)
+
+
+# Oracle parity first: with `-x` a failure in a later (multi-GPU / partition) file must not hide the parity tests.
+_ORDER = ["test_oracle", "test_abi", "test_sort_gpu", "test_vs_reference_gpu", "test_cxx_shims"]
+
+
+def pytest_collection_modifyitems(session, config, items):
+    def rank(item):
+        name = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+        return _ORDER.index(name) if name in _ORDER else len(_ORDER)
+
+    items.sort(key=rank)  # stable: keeps the order inside each file
