@@ -249,6 +249,7 @@ struct PassArgs
   int num_splitters;
   unsigned long long splitters[15];
   const PeerTable* peer; // bucket mode: remote destinations (device memory), or nullptr for keys_out / vals_out
+  int sm_count;          // SMs of the current device (grid size of the persistent kernel)
 };
 
 } // namespace b200rs

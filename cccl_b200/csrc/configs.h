@@ -25,8 +25,13 @@ struct OnesweepConfig
 // index 0 is the default for the (key_bytes, value_bytes) combination
 const OnesweepConfig* onesweep_configs_k1(int value_bytes, int* count);
 const OnesweepConfig* onesweep_configs_k2(int value_bytes, int* count);
-const OnesweepConfig* onesweep_configs_k4(int value_bytes, int* count);
-const OnesweepConfig* onesweep_configs_k8(int value_bytes, int* count);
+// 4- and 8-byte keys: one translation unit per value-width group so that the library builds in parallel
+const OnesweepConfig* onesweep_configs_k4_v0(int* count);
+const OnesweepConfig* onesweep_configs_k4_v4(int* count);
+const OnesweepConfig* onesweep_configs_k4_vx(int value_bytes, int* count);
+const OnesweepConfig* onesweep_configs_k8_v0(int* count);
+const OnesweepConfig* onesweep_configs_k8_v4(int* count);
+const OnesweepConfig* onesweep_configs_k8_vx(int value_bytes, int* count);
 
 cudaError_t launch_histogram(
   const void* keys, unsigned long long n, int key_bytes, unsigned long long* bins, int passes, int begin_bit,

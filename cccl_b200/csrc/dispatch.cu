@@ -81,9 +81,13 @@ static const OnesweepConfig* configs_for(int key_bytes, int value_bytes, int* co
     case 2:
       return onesweep_configs_k2(value_bytes, count);
     case 4:
-      return onesweep_configs_k4(value_bytes, count);
+      return value_bytes == 0   ? onesweep_configs_k4_v0(count)
+             : value_bytes == 4 ? onesweep_configs_k4_v4(count)
+                                : onesweep_configs_k4_vx(value_bytes, count);
     case 8:
-      return onesweep_configs_k8(value_bytes, count);
+      return value_bytes == 0   ? onesweep_configs_k8_v0(count)
+             : value_bytes == 4 ? onesweep_configs_k8_v4(count)
+                                : onesweep_configs_k8_vx(value_bytes, count);
     default:
       *count = 0;
       return nullptr;
@@ -585,12 +589,16 @@ int b200rs_sort(
       a.all_ones     = 0xffffffffu;
       a.shift        = bit;
       a.mask         = (1u << nbits) - 1u;
-      a.first_pass   = pass == 0;
-      a.last_pass    = pass == passes - 1;
-      a.big          = (num_items >> 32) != 0 || g_force_big.load(std::memory_order_relaxed);
+      // unsigned ascending keys: the transform is the identity, the kernels skip it altogether
+      const bool identity = xf.float_mask == 0 && xf.sign_mask == 0 && xf.desc_mask == 0;
+      a.first_pass   = pass == 0 && !identity;
+      a.last_pass    = pass == passes - 1 && !identity;
+      // 64-bit output offsets from 2^32 - 2^16 items on: the folded scatter biases its 32-bit offsets by one tile
+      a.big          = ((num_items + 65536) >> 32) != 0 || g_force_big.load(std::memory_order_relaxed);
       a.xf           = xf;
       a.num_splitters = 0;
       a.peer          = nullptr;
+      a.sm_count      = sms;
       mark_op(stream, OP_ONESWEEP);
       e = cfg->launch(a, tiles, stream);
       if (e != cudaSuccess)
@@ -770,7 +778,8 @@ static int partition_impl(
   {
     a.splitters[i] = h_splitters[i];
   }
-  a.peer = remote ? reinterpret_cast<const PeerTable*>(base + off_peer) : nullptr;
+  a.peer     = remote ? reinterpret_cast<const PeerTable*>(base + off_peer) : nullptr;
+  a.sm_count = sms;
   mark_op(stream, OP_ONESWEEP);
   e = cfg->launch_bucket(a, unsigned(tiles), stream);
   mark_end(stream);

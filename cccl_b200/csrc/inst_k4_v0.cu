@@ -1,0 +1,33 @@
+// onesweep instantiations for 4-byte keys (u32 / i32 / f32), keys only.  Index 0 of each table is the default configuration; the others are kept
+// for A/B measurement (tools/sweep.py) and are all covered by the parity tests.
+#include "inst.cuh"
+
+namespace b200rs
+{
+using K = uint32_t;
+#define C(VB, NT, IPT, MINB) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB>()
+#define O(VB, NT, IPT, MINB, OPT) make_config<K, VB, NT, IPT, RANK_BALLOT, MINB, OPT>()
+#define OB(VB, NT, IPT, MINB, OPT) make_config_with_bucket<K, VB, NT, IPT, RANK_BALLOT, MINB, OPT>()
+#define T(VB, NT, IPT, MINB, LBW) make_tma_config<K, VB, NT, IPT, MINB, LBW>()
+// 7 = FMA-pipe complement + look-back window + 16-bit counters; FAST adds the single-digit-warp short circuit and, for
+// 4-byte keys, the folded table addressing (onesweep.cuh OnesweepOpt)
+constexpr int BASE = OPT_FMA_NOT | OPT_LB_WINDOW | OPT_CTR16;
+constexpr int FAST = BASE | OPT_SHORT_WARP | OPT_FOLD | OPT_FOLD_PTR;
+
+static const OnesweepConfig cfg_v0[] = {
+  OB(0, 256, 44, 3, FAST),
+  O(0, 256, 40, 3, BASE),                  // the round-1 default
+  C(0, 256, 32, 4),                        // no optimisation switch at all
+  T(0, 512, 32, 2, 4),                     // TMA bulk-store scatter
+  O(0, 256, 44, 3, FAST | OPT_SHORT_TILE), // + single-digit-tile copy
+  O(0, 256, 40, 3, FAST)
+};
+#define B200RS_TABLE(arr)                     \
+  *count = int(sizeof(arr) / sizeof(arr[0])); \
+  return arr
+
+const OnesweepConfig* onesweep_configs_k4_v0(int* count)
+{
+  B200RS_TABLE(cfg_v0);
+}
+} // namespace b200rs

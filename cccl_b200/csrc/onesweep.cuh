@@ -48,7 +48,17 @@ enum OnesweepOpt
   OPT_FMA_NOT   = 1, // per-lane ballot complement as a predicated IMAD (FMA pipe) instead of LOP3 (ALU pipe)
   OPT_LB_WINDOW = 2, // look-back polls 8 predecessors per round trip
   OPT_CTR16     = 4, // 16-bit warp counters: half the words per bank, fewer shared-memory bank conflicts
-  OPT_BUCKET    = 8  // the digit is the key's destination bucket against PassArgs::splitters (multi-GPU partition pass)
+  OPT_BUCKET    = 8, // the digit is the key's destination bucket against PassArgs::splitters (multi-GPU partition pass)
+  // (bits 16 and 32 were a hand-pipelined staging loop and an early look-back request: measured 3 % slower / neutral
+  //  on B200, removed -- DESIGN.md section 6)
+  // single-digit short circuits (reference: agent_radix_sort_onesweep.cuh:386-467)
+  OPT_SHORT_WARP  = 64,  // a warp whose keys share one digit skips ranking
+  OPT_SHORT_TILE  = 128, // a full tile whose keys share one digit skips staging and is copied straight to its run
+  OPT_SHORT       = 64 + 128,
+  // 4-byte keys, 16-bit counters: the digit is extracted already scaled and merged with the table base (one rotate +
+  // one LOP3 give the shared-memory address), and the scatter folds the staged position into a per-thread pointer
+  OPT_FOLD        = 256,
+  OPT_FOLD_PTR    = 512 // with OPT_FOLD: scatter through a per-thread pointer + biased offsets instead of offset + position
 };
 
 template <class U, int VBYTES, int NT, int IPT, int OPT = 0>
@@ -341,8 +351,98 @@ __device__ __forceinline__ void match_digit_ballot_fma(uint32_t d, uint32_t ones
     : "r"(d), "r"(ones));
 }
 
+// OPT_FOLD: shared-memory address of a 4-byte key's table entry.  rot = (shift - log2(entry bytes)) & 31,
+// scaled_mask = digit mask << log2(entry bytes), base aligned to 256 * entry bytes.
+template <bool FLOATK>
+__device__ __forceinline__ uint32_t
+digit_entry(uint32_t key, uint32_t rot, uint32_t scaled_mask, uint32_t base, uint32_t neg_zero, uint32_t pos_zero)
+{
+  if (FLOATK)
+  {
+    key = key == neg_zero ? pos_zero : key;
+  }
+  return (__funnelshift_r(key, key, rot) & scaled_mask) | base;
+}
+
+// match-by-ballot on the digit held in bits [1, 9) of a 16-bit-counter address (OPT_FOLD)
+__device__ __forceinline__ void match_entry_ballot_fma(uint32_t e, uint32_t ones, uint32_t& b, uint32_t& c)
+{
+  asm volatile(
+    "{\n"
+    ".reg .pred p0, p1, p2, p3;\n"
+    ".reg .b32 v0, v1, v2, v3, v4, v5, v6, v7, t, dh;\n"
+    "shr.u32 dh, %2, 5;\n"
+    "and.b32 t, %2, 2; setp.ne.u32 p0, t, 0;\n"
+    "and.b32 t, %2, 4; setp.ne.u32 p1, t, 0;\n"
+    "and.b32 t, %2, 8; setp.ne.u32 p2, t, 0;\n"
+    "and.b32 t, %2, 16; setp.ne.u32 p3, t, 0;\n"
+    "vote.sync.ballot.b32 v0, p0, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v1, p1, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v2, p2, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v3, p3, 0xffffffff;\n"
+    "@!p0 mad.lo.u32 v0, v0, %3, %3;\n"
+    "@!p1 mad.lo.u32 v1, v1, %3, %3;\n"
+    "@!p2 mad.lo.u32 v2, v2, %3, %3;\n"
+    "@!p3 mad.lo.u32 v3, v3, %3, %3;\n"
+    "and.b32 t, dh, 1; setp.ne.u32 p0, t, 0;\n"
+    "and.b32 t, dh, 2; setp.ne.u32 p1, t, 0;\n"
+    "and.b32 t, dh, 4; setp.ne.u32 p2, t, 0;\n"
+    "and.b32 t, dh, 8; setp.ne.u32 p3, t, 0;\n"
+    "vote.sync.ballot.b32 v4, p0, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v5, p1, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v6, p2, 0xffffffff;\n"
+    "vote.sync.ballot.b32 v7, p3, 0xffffffff;\n"
+    "@!p0 mad.lo.u32 v4, v4, %3, %3;\n"
+    "@!p1 mad.lo.u32 v5, v5, %3, %3;\n"
+    "@!p2 mad.lo.u32 v6, v6, %3, %3;\n"
+    "@!p3 mad.lo.u32 v7, v7, %3, %3;\n"
+    "lop3.b32 t, v0, v1, v2, 0x80;\n"
+    "lop3.b32 %0, v3, v4, v5, 0x80;\n"
+    "lop3.b32 %1, v6, v7, t, 0x80;\n"
+    "}\n"
+    : "=r"(b), "=r"(c)
+    : "r"(e), "r"(ones));
+}
+
 // Decoupled look-back of one digit over the predecessor tiles (status words `base[t * RADIX]`, t < tile), W words per
 // round trip.  Each word carries its own flags, so the loads need no ordering among themselves.
+template <int W>
+__device__ __forceinline__ void lookback_load(const uint32_t* base, int t, uint32_t (&w)[W])
+{
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+  {
+    w[j] = (t - j >= 0) ? ld_relaxed_u32(base + size_t(t - j) * RADIX) : LB_INCLUSIVE;
+  }
+}
+
+// Folds one window into `prefix`; returns true once an inclusive prefix was reached, else moves t to the first word
+// that was not published yet.
+template <int W>
+__device__ __forceinline__ bool lookback_consume(const uint32_t (&w)[W], uint32_t& prefix, int& t)
+{
+  int state = 0, used = 0; // 0 consuming, 1 met a word that is not published yet, 2 reached an inclusive prefix
+#pragma unroll
+  for (int j = 0; j < W; ++j)
+  {
+    if (state == 0)
+    {
+      if ((w[j] & LB_FLAG_MASK) == 0)
+      {
+        state = 1;
+      }
+      else
+      {
+        prefix += w[j] & LB_VALUE_MASK;
+        ++used;
+        state = (w[j] & LB_INCLUSIVE) ? 2 : 0;
+      }
+    }
+  }
+  t -= used;
+  return state == 2;
+}
+
 template <int W>
 __device__ __forceinline__ uint32_t lookback_prefix(const uint32_t* base, uint32_t tile)
 {
@@ -351,41 +451,26 @@ __device__ __forceinline__ uint32_t lookback_prefix(const uint32_t* base, uint32
   while (true)
   {
     uint32_t w[W];
-#pragma unroll
-    for (int j = 0; j < W; ++j)
-    {
-      w[j] = (t - j >= 0) ? ld_relaxed_u32(base + size_t(t - j) * RADIX) : LB_INCLUSIVE;
-    }
-    int state = 0, used = 0; // 0 consuming, 1 met a word that is not published yet, 2 reached an inclusive prefix
-#pragma unroll
-    for (int j = 0; j < W; ++j)
-    {
-      if (state == 0)
-      {
-        if ((w[j] & LB_FLAG_MASK) == 0)
-        {
-          state = 1;
-        }
-        else
-        {
-          prefix += w[j] & LB_VALUE_MASK;
-          ++used;
-          state = (w[j] & LB_INCLUSIVE) ? 2 : 0;
-        }
-      }
-    }
-    if (state == 2)
+    lookback_load<W>(base, t, w);
+    if (lookback_consume<W>(w, prefix, t))
     {
       return prefix;
     }
-    t -= used;
   }
 }
 
-// The tile body.  FULL: every item of the tile is valid (all tiles but possibly the last one of a portion).
-template <class U, int VBYTES, int NT, int IPT, int RANK, int OPT, bool FLOATK, bool BIG, bool FULL>
+struct NoHook
+{
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// SMEM_IN: the tile's keys were bulk-copied to shared memory at s_in (persistent kernel).  s_stage != 0: staging area
+// (the persistent kernel stages in place).  after_rank() runs once every key of the tile is in a register and ranked.
+template <class U, int VBYTES, int NT, int IPT, int RANK, int OPT, bool FLOATK, bool BIG, bool FULL, bool SMEM_IN = false,
+          class Hook = NoHook>
 __device__ __forceinline__ void onesweep_tile(
-  const PassArgs& a, const uint32_t sbase, const uint32_t tile, const uint32_t tile_base, const uint32_t valid)
+  const PassArgs& a, const uint32_t sbase, const uint32_t tile, const uint32_t tile_base, const uint32_t valid,
+  const uint32_t s_in = 0, const uint32_t s_stage = 0, Hook after_rank = Hook())
 {
   using L = OnesweepSmem<U, VBYTES, NT, IPT, OPT>;
   using V = typename value_of<VBYTES>::type;
@@ -393,6 +478,13 @@ __device__ __forceinline__ void onesweep_tile(
   constexpr bool C16     = (OPT & OPT_CTR16) != 0;
   constexpr bool BUCKET  = (OPT & OPT_BUCKET) != 0;
   constexpr uint32_t CB  = L::CTR_BYTES;
+  constexpr bool FOLD    = (OPT & OPT_FOLD) != 0 && sizeof(U) == 4 && C16 && !BUCKET && RANK == RANK_BALLOT;
+  constexpr bool FOLDP   = FOLD && (OPT & OPT_FOLD_PTR) != 0 && !BIG;
+  // OPT_FOLD: the warp counters, ranks and staged positions are kept in BYTES of 4-byte items (no shift when a key is
+  // staged; the rank is one IMAD on the FMA pipe).  CSH converts them back to items.
+  constexpr bool FOLDB   = FOLD && L::TILE * 4 < 65536;
+  constexpr int CSH      = FOLDB ? 2 : 0;
+  static_assert(!FOLD || (L::OFF_WARP % 512 == 0 && L::OFF_GOFF % 1024 == 0), "folded table bases must be aligned");
 
   const uint32_t tid   = threadIdx.x;
   const uint32_t lane  = tid & 31;
@@ -404,8 +496,18 @@ __device__ __forceinline__ void onesweep_tile(
   const uint32_t s_warp = sbase + L::OFF_WARP;
   const uint32_t s_goff = sbase + L::OFF_GOFF;
   const uint32_t s_misc = sbase + L::OFF_MISC;
-  const uint32_t s_data = sbase + L::OFF_DATA;
+  const uint32_t s_data = s_stage != 0 ? s_stage : sbase + L::OFF_DATA;
   const uint32_t s_mine = s_warp + warp * (RADIX * CB); // this warp's running offsets
+  // OPT_FOLD: rotate amounts and scaled masks of the two tables addressed by digit (16-bit counters, 32-bit offsets)
+  const uint32_t rot_ctr  = uint32_t(shift + 31) & 31u;
+  const uint32_t rot_goff = uint32_t(shift + 30) & 31u;
+  const uint32_t msk_ctr  = dmask << 1;
+  const uint32_t msk_goff = dmask << 2;
+
+  if (FOLD && (sbase & 1023u) != 0)
+  {
+    __trap(); // the folded table addressing relies on the 1024-byte alignment of the dynamic shared memory
+  }
 
   // ---- load keys, warp-striped
   U key[IPT];
@@ -415,7 +517,14 @@ __device__ __forceinline__ void onesweep_tile(
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
     {
-      key[i] = (FULL || chunk + i * 32 < valid) ? kin[i * 32] : U(0);
+      if (SMEM_IN)
+      {
+        key[i] = lds_t<U>(s_in + (chunk + i * 32) * uint32_t(sizeof(U)));
+      }
+      else
+      {
+        key[i] = (FULL || chunk + i * 32 < valid) ? kin[i * 32] : U(0);
+      }
     }
     if (a.first_pass)
     {
@@ -447,26 +556,70 @@ __device__ __forceinline__ void onesweep_tile(
   uint32_t bid[BUCKET ? (IPT + 3) / 4 : 1];
   const uint32_t lt_mask = lanemask_lt();
   const uint32_t gt_mask = lanemask_gt();
+  // single-digit warp: when all 32 * IPT keys of the warp share one digit their ranks are their positions.  The test
+  // costs the normal path one shuffle, one compare and one vote per warp and tile (the full check only runs when the
+  // first row already agrees).
+  bool warp_single = false;
+  if ((OPT & OPT_SHORT_WARP) && !BUCKET)
+  {
+    const uint32_t d0    = tile_digit<FLOATK, BUCKET>(a, key[0], shift, dmask, neg_zero, pos_zero);
+    const uint32_t first = __shfl_sync(0xffffffffu, d0, 0);
+    if (__all_sync(0xffffffffu, d0 == first))
+    {
+      uint32_t diff = 0;
+#pragma unroll
+      for (int i = 1; i < IPT; ++i)
+      {
+        diff |= tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero) ^ first;
+      }
+      warp_single = __all_sync(0xffffffffu, diff == 0);
+      if (warp_single)
+      {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i)
+        {
+          put16(rank2, i, (uint32_t(i) * 32u + lane + 1u) << CSH);
+        }
+        if (lane == 0)
+        {
+          ctr_st<C16>(s_mine + first * CB, (32u * IPT) << CSH);
+        }
+      }
+    }
+  }
+  if (!warp_single)
+  {
 #pragma unroll
   for (int i = 0; i < IPT; ++i)
   {
-    const uint32_t d      = tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
+    uint32_t d = 0, ctr;
     uint32_t b, c; // peers == b & c
-    if (RANK == RANK_MATCH)
+    if (FOLD)
     {
-      b = c = __match_any_sync(0xffffffffu, d);
-    }
-    else if (OPT & OPT_FMA_NOT)
-    {
-      match_digit_ballot_fma(d, a.all_ones, b, c);
+      ctr = digit_entry<FLOATK>(uint32_t(key[i]), rot_ctr, msk_ctr, s_mine, uint32_t(neg_zero), uint32_t(pos_zero));
+      match_entry_ballot_fma(ctr, a.all_ones, b, c);
     }
     else
     {
-      match_digit_ballot(d, b, c);
+      d   = tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
+      ctr = s_mine + d * CB;
+      if (RANK == RANK_MATCH)
+      {
+        b = c = __match_any_sync(0xffffffffu, d);
+      }
+      else if (OPT & OPT_FMA_NOT)
+      {
+        match_digit_ballot_fma(d, a.all_ones, b, c);
+      }
+      else
+      {
+        match_digit_ballot(d, b, c);
+      }
     }
-    const uint32_t before = __popc(b & c & lt_mask);
-    const uint32_t ctr    = s_mine + d * CB;
-    const uint32_t next   = ctr_ld<C16>(ctr) + before + 1;
+    // position of the key among the warp's keys of its digit, + 1 (in bytes with OPT_FOLD: peers up to and including
+    // this lane, times 4, on top of the running count)
+    const uint32_t next = FOLDB ? ctr_ld<C16>(ctr) + 4u * uint32_t(__popc(b & c & ~gt_mask))
+                                : ctr_ld<C16>(ctr) + uint32_t(__popc(b & c & lt_mask)) + 1u;
     if ((b & c & gt_mask) == 0) // highest peer lane: its position + 1 is the new running count
     {
       ctr_st<C16>(ctr, next);
@@ -478,6 +631,8 @@ __device__ __forceinline__ void onesweep_tile(
       bid[i / 4] = (i & 3) == 0 ? d : (bid[i / 4] | (d << (8 * (i & 3))));
     }
   }
+  }
+  after_rank();
   __syncthreads();
 
   // ---- per-digit tile totals (one thread per digit), publish, block-wide exclusive scan over digits
@@ -490,7 +645,7 @@ __device__ __forceinline__ void onesweep_tile(
     {
       total += ctr_ld<C16>(s_warp + (w * RADIX + tid) * CB);
     }
-    st_relaxed_u32(lb_word, (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | total);
+    st_relaxed_u32(lb_word, (tile == 0 ? LB_INCLUSIVE : LB_PARTIAL) | (total >> CSH));
     uint32_t incl = total;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1)
@@ -506,6 +661,10 @@ __device__ __forceinline__ void onesweep_tile(
       sts32(s_misc + warp * 4, incl);
     }
     excl = incl - total;
+    if ((OPT & OPT_SHORT_TILE) && FULL && !BUCKET && total == (uint32_t(L::TILE) << CSH))
+    {
+      sts32(s_misc + 44, 0x100u | tid); // single-digit tile (the word was cleared before the tile started)
+    }
   }
   __syncthreads();
   if (tid < RADIX)
@@ -528,23 +687,41 @@ __device__ __forceinline__ void onesweep_tile(
   }
   __syncthreads();
 
+  // single-digit tile: every key goes to one run in tile order -- no staging, no per-key offset look-up
+  const bool short_tile = (OPT & OPT_SHORT_TILE) && FULL && !BUCKET && lds32(s_misc + 44) != 0;
+
   // ---- stage keys in shared memory in digit order (ranks are + 1: stage one item below s_data)
-#pragma unroll
-  for (int i = 0; i < IPT; ++i)
+  if (short_tile)
   {
-    const uint32_t d = BUCKET ? ((bid[i / 4] >> (8 * (i & 3))) & 0xffu)
-                              : tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
-    const uint32_t r = get16(rank2, i) + ctr_ld<C16>(s_mine + d * CB);
-    if (VBYTES > 0)
+  }
+  else
+  {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
     {
-      update16(rank2, i, r);
+      uint32_t centry;
+      if (FOLD)
+      {
+        centry = digit_entry<FLOATK>(uint32_t(key[i]), rot_ctr, msk_ctr, s_mine, uint32_t(neg_zero), uint32_t(pos_zero));
+      }
+      else
+      {
+        const uint32_t d = BUCKET ? ((bid[i / 4] >> (8 * (i & 3))) & 0xffu)
+                                  : tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
+        centry           = s_mine + d * CB;
+      }
+      const uint32_t r = get16(rank2, i) + ctr_ld<C16>(centry);
+      if (VBYTES > 0)
+      {
+        update16(rank2, i, r);
+      }
+      sts_t<U>(s_data - uint32_t(sizeof(U)) + (FOLDB ? r : r * uint32_t(sizeof(U))), key[i]);
     }
-    sts_t<U>(s_data - uint32_t(sizeof(U)) + r * uint32_t(sizeof(U)), key[i]);
   }
 
   // values are fetched now so their latency hides behind the look-back
   V val[VBYTES > 0 ? IPT : 1];
-  if (VBYTES > 0)
+  if (VBYTES > 0 && !short_tile)
   {
     const V* vin = static_cast<const V*>(a.vals_in) + tile_base + chunk;
 #pragma unroll
@@ -585,8 +762,10 @@ __device__ __forceinline__ void onesweep_tile(
           w -= RADIX;
         }
       }
-      st_relaxed_u32(lb_word, LB_INCLUSIVE | (prefix + total));
+      st_relaxed_u32(lb_word, LB_INCLUSIVE | (prefix + (total >> CSH)));
     }
+    total >>= CSH; // items from here on
+    excl >>= CSH;
     const unsigned long long gbase = a.bins[tid] + prefix;
     // element offset such that out[off + staged position] is the output slot (wraps consistently when negative)
     if (BIG)
@@ -595,7 +774,9 @@ __device__ __forceinline__ void onesweep_tile(
     }
     else
     {
-      sts32(s_goff + tid * 4, uint32_t(gbase) - excl);
+      // OPT_FOLD biases the offsets by one tile so that they never wrap below zero (the scatter adds them to a
+      // 64-bit pointer); the host selects the 64-bit-offset kernels early enough that the bias cannot overflow
+      sts32(s_goff + tid * 4, uint32_t(gbase) - excl + (FOLDP ? uint32_t(L::TILE) : 0u));
     }
     if (BUCKET)
     {
@@ -608,9 +789,52 @@ __device__ __forceinline__ void onesweep_tile(
   }
   __syncthreads();
 
+  U* kout = static_cast<U*>(a.keys_out);
+  if (short_tile)
+  {
+    // the run of the tile's one digit starts at goff (its exclusive prefix inside the tile is zero); tile order is kept
+    const uint32_t d = lds32(s_misc + 44) & 0xffu;
+    const XformT<U> xf(a.xf);
+    const unsigned long long g = (BIG ? lds64(s_goff + d * 8)
+                                      : (unsigned long long) (lds32(s_goff + d * 4) - (FOLDP ? uint32_t(L::TILE) : 0u)))
+                               + chunk;
+    U* ko = kout + g;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+      ko[i * 32] = a.last_pass ? twiddle_out(key[i], xf) : key[i];
+    }
+    if (VBYTES > 0)
+    {
+      const V* vin = static_cast<const V*>(a.vals_in) + tile_base + chunk;
+      V* vo        = static_cast<V*>(a.vals_out) + g;
+#pragma unroll
+      for (int i0 = 0; i0 < IPT; i0 += 8)
+      {
+        V v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+          if (i0 + j < IPT)
+          {
+            v[j] = vin[(i0 + j) * 32];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+          if (i0 + j < IPT)
+          {
+            vo[(i0 + j) * 32] = v[j];
+          }
+        }
+      }
+    }
+    return;
+  }
+
   // ---- coalesced scatter: consecutive threads write consecutive staged positions
   uint32_t digs[(IPT + 3) / 4];
-  U* kout = static_cast<U*>(a.keys_out);
   auto store_keys = [&](auto last_tag) {
     constexpr bool LAST = decltype(last_tag)::value;
     const XformT<U> xf(a.xf);
@@ -634,12 +858,33 @@ __device__ __forceinline__ void onesweep_tile(
           }
           d = cur;
         }
+        else if (FOLD && !BIG)
+        {
+          // nothing: the offset entry is addressed straight from the key below
+        }
         else
         {
           d = tile_digit<FLOATK, BUCKET>(a, k, shift, dmask, neg_zero, pos_zero);
         }
         const U o = LAST ? twiddle_out(k, xf) : k;
-        if (BIG)
+        if (FOLD && !BIG)
+        {
+          const uint32_t ge =
+            digit_entry<FLOATK>(uint32_t(k), rot_goff, msk_goff, s_goff, uint32_t(neg_zero), uint32_t(pos_zero));
+          if (VBYTES > 0)
+          {
+            d = (ge >> 2) & 0xffu;
+          }
+          if (FOLDP)
+          {
+            (kout + ptrdiff_t(tid) - ptrdiff_t(L::TILE))[size_t(lds32(ge)) + size_t(i * NT)] = o;
+          }
+          else
+          {
+            kout[lds32(ge) + pos] = o;
+          }
+        }
+        else if (BIG)
         {
           kout[lds64(s_goff + d * 8) + pos] = o;
         }
@@ -681,7 +926,7 @@ __device__ __forceinline__ void onesweep_tile(
     {
       if (FULL || chunk + i * 32 < valid)
       {
-        sts_t<V>(s_data - uint32_t(sizeof(V)) + get16(rank2, i) * uint32_t(sizeof(V)), val[i]);
+        sts_t<V>(s_data - uint32_t(sizeof(V)) + (get16(rank2, i) >> CSH) * uint32_t(sizeof(V)), val[i]);
       }
     }
     __syncthreads();
@@ -704,6 +949,10 @@ __device__ __forceinline__ void onesweep_tile(
                                              uint32_t(offsetof(PeerTable, rank_dst_vals)), d,
                                              lds32(s_goff + d * 4) + pos, uint32_t(sizeof(V)))) = v;
         }
+        else if (FOLDP)
+        {
+          (vout + ptrdiff_t(tid) - ptrdiff_t(L::TILE))[size_t(lds32(s_goff + d * 4)) + size_t(i * NT)] = v;
+        }
         else
         {
           vout[lds32(s_goff + d * 4) + pos] = v;
@@ -712,14 +961,6 @@ __device__ __forceinline__ void onesweep_tile(
     }
   }
 
-  // the chained-scan status words of the NEXT launch are zeroed by this one, off the critical path
-  if (tid < RADIX && a.lookback_next != nullptr)
-  {
-    for (uint32_t t = tile; t < a.lookback_next_tiles; t += gridDim.x)
-    {
-      a.lookback_next[size_t(t) * RADIX + tid] = 0;
-    }
-  }
 }
 
 template <class U, int VBYTES, int NT, int IPT, int RANK, int MINB, int OPT, bool FLOATK, bool BIG>
@@ -730,7 +971,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
   static_assert(NT >= RADIX && NT % 32 == 0, "one thread per digit is required");
   static_assert(TILE < 65536, "staged positions (+1) are kept in 16 bits");
 
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
   const uint32_t tid   = threadIdx.x;
 
@@ -738,6 +979,7 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
   if (tid == 0)
   {
     sts32(sbase + L::OFF_MISC + 32, atomicAdd(a.tile_counter, 1u));
+    sts32(sbase + L::OFF_MISC + 44, 0); // single-digit-tile flag
   }
   {
     // zero the warp counters: NW * 256 counters of CTR_BYTES each, as 32-bit words
@@ -768,6 +1010,14 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
   else
   {
     onesweep_tile<U, VBYTES, NT, IPT, RANK, OPT, FLOATK, BIG, false>(a, sbase, tile, tile_base, valid);
+  }
+  // the chained-scan status words of the NEXT launch are zeroed by this one, off the critical path
+  if (tid < RADIX && a.lookback_next != nullptr)
+  {
+    for (uint32_t t = tile; t < a.lookback_next_tiles; t += gridDim.x)
+    {
+      a.lookback_next[size_t(t) * RADIX + tid] = 0;
+    }
   }
 }
 

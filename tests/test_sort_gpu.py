@@ -210,13 +210,17 @@ def test_every_compiled_config_is_correct():
     try:
         for kdt, vdt in ((np.uint32, None), (np.uint32, np.uint32), (np.uint64, None), (np.uint64, np.uint32)):
             n_cfg = len(_native.describe_configs(np.dtype(kdt).itemsize, np.dtype(vdt).itemsize if vdt else 0))
-            k = make_keys("entropy2", 200_003, kdt, seed=77)
-            for c in range(n_cfg):
-                lib.b200rs_set_config(c)
-                if vdt is None:
-                    check_keys(k)
-                else:
-                    check_pairs(k, make_values(k.size, vdt))
+            # all-equal / two-value inputs drive the single-digit short circuits (reference:
+            # agent_radix_sort_onesweep.cuh:386-467) of the configurations that have them
+            for dist in ("entropy2", "equal", "few2"):
+                k = make_keys(dist, 200_003, kdt, seed=77)
+                for c in range(n_cfg):
+                    lib.b200rs_set_config(c)
+                    if vdt is None:
+                        check_keys(k)
+                        check_keys(k, descending=True)
+                    else:
+                        check_pairs(k, make_values(k.size, vdt))
     finally:
         lib.b200rs_set_config(-1)
 
