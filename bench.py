@@ -179,7 +179,9 @@ def cub_same_gpu(kdt, vb, log2n, dist, desc, b, e, iters=10):
     kt = {"uint32": "u32", "uint64": "u64", "float32": "f32", "int64": "i64"}[kdt]
     if not os.path.exists(exe) or vb not in (0, 4, 8):
         return None
-    rounds = int(dist[7:]) if dist.startswith("entropy") else 1
+    # the tool's own generators: AND rounds for the entropy rows, equal / fewK / sorted by name (uniform otherwise)
+    rounds = dist[7:] if dist.startswith("entropy") else (dist if dist == "equal" or dist == "sorted"
+                                                          or dist.startswith("few") else "1")
     try:
         out = subprocess.run([exe, "bench", kt, str(vb), str(log2n), str(int(desc)), str(b), str(e), str(rounds),
                               str(iters)], capture_output=True, text=True, timeout=300).stdout
@@ -244,6 +246,74 @@ def make_device_input(torch, np, name):
     if vdt is not None:
         vals = torch.arange(n, dtype=torch.int32, device="cuda").view(torch.uint8)
     return keys, vals
+
+
+def device_leg(name, steps, warmup, with_cub=True):
+    """Device-resident timing of one named workload (inputs in HBM, temp pre-allocated, CUDA events): the compact
+    record that the default bench line carries for every BASELINE config besides the headline one."""
+    import numpy as np
+    import torch
+
+    from cccl_b200 import _native
+    from cccl_b200.radix_sort import key_kind_of
+
+    kdt, vdt, log2n, dist, desc, b, e = WORKLOADS[name]
+    n = 1 << log2n
+    kb = np.dtype(kdt).itemsize
+    vb = np.dtype(vdt).itemsize if vdt else 0
+    kind = key_kind_of(np.dtype(kdt))
+    lib = _native.lib()
+    keys, vals = make_device_input(torch, np, name)
+    keys_out = torch.empty_like(keys)
+    vals_out = torch.empty_like(vals) if vals is not None else None
+    p = lambda t: t.data_ptr() if t is not None else 0
+    stream = torch.cuda.current_stream().cuda_stream
+    need, _ = _native.sort_raw(0, 0, p(keys), p(keys_out), p(vals), p(vals_out), n, kind, kb, vb, b, e, desc, False,
+                               stream)
+    temp = torch.empty(need, dtype=torch.uint8, device="cuda")
+
+    def step():
+        _native.sort_raw(temp.data_ptr(), need, p(keys), p(keys_out), p(vals), p(vals_out), n, kind, kb, vb, b, e,
+                         desc, False, stream)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    lib.b200rs_timing_enable(1)
+    step()
+    ops = _native.timing_read()
+    lib.b200rs_timing_enable(0)
+    one = [t for o, t in ops if o == "onesweep"]
+    peak, _ = measured_peaks()
+    whole = algorithmic_bytes_per_item(kb, vb, e - b) * n
+    rec = {"workload": name, "value": n / (ms * 1e-3) / 1e9, "unit": "Gkeys/s", "ms_per_step": ms,
+           "onesweep_ms": sum(one) / len(one), "onesweep_frac": 2.0 * n * (kb + vb) / (sum(one) / len(one) * 1e-3) / 1e9 / peak,
+           "whole_sort_frac": whole / (ms * 1e-3) / 1e9 / peak, "steps": steps,
+           "tile_config": _native.describe_configs(kb, vb)[0]}
+    del keys, vals, keys_out, vals_out, temp
+    torch.cuda.empty_cache()
+    if with_cub:
+        c = cub_same_gpu(kdt, vb, log2n, dist, desc, b, e, iters=5)
+        rec["cub_same_gpu"] = c.get("value") if c and "value" in c else None
+    return rec
+
+
+# every other BASELINE.json config (C3 uniform / entropy 0.201, C4 f32 and i64 descending on a bit window and on all
+# bits), the like-for-like anchor of the multi-GPU arm, and the skew rows of SURVEY.md 10.16
+EXTRA_WORKLOADS = [
+    "sortpairs_u64_u32_2^28_uniform", "sortpairs_u64_u32_2^28_entropy0.201",
+    "sortkeys_f32_desc_2^28_bits8_24", "sortkeys_f32_desc_2^28",
+    "sortkeys_i64_desc_2^28_bits16_48", "sortkeys_i64_desc_2^28",
+    "sortpairs_u32_u32_2^28_uniform",
+    "sortkeys_u32_2^28_entropy0.201", "sortkeys_u32_2^28_equal", "sortkeys_u32_2^28_few16", "sortkeys_u32_2^28_sorted",
+]
 
 
 def run_single_gpu(args):
@@ -424,6 +494,18 @@ def run_single_gpu(args):
 
     cub = None if args.no_cub else cub_same_gpu(kdt, vb, log2n, dist, desc, b, e)
 
+    # the other BASELINE configs and the skew rows, device-resident, so that the driver's own run times them too
+    extra = None
+    if args.workload is None and not args.no_extra:
+        del slots, sorter, keys, keys_out, vals, vals_out, temp, d_in, d_out, d_vin, d_vout, kw
+        torch.cuda.empty_cache()
+        extra = []
+        for w in EXTRA_WORKLOADS:
+            try:
+                extra.append(device_leg(w, max(3, min(args.steps, 10)), 3, with_cub=not args.no_cub))
+            except Exception as ex:  # reported, never fatal for the headline line
+                extra.append({"workload": w, "error": str(ex)[:200]})
+
     line = {
         "metric": METRIC,
         "value": value,
@@ -449,6 +531,7 @@ def run_single_gpu(args):
         "gpu_launches_per_step": launches_per_step,
         "per_op_ms": {k: sum(v) / len(v) for k, v in per_op.items()},
         "clocks": clocks.summary(),
+        "extra_workloads": extra,
     }
     print(json.dumps(line))
 
@@ -477,6 +560,7 @@ def main():
     ap.add_argument("--config", type=int, default=None, help="force an onesweep tile configuration index")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cub", action="store_true", help="skip the cub-on-the-same-GPU context run")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads legs of the default line")
     ap.add_argument("--log2-per-gpu", type=int, default=28, help="multi-GPU: log2 of pairs per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

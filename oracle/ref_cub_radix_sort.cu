@@ -7,7 +7,10 @@
 //   (2) context number: time cub::DeviceRadixSort on the same GPU and inputs as bench.py ("cub on same GPU").
 //
 // usage: ref_cub_radix_sort sort  <ktype> <vbytes> <n> <desc> <begin_bit> <end_bit> <keys.bin> <vals.bin|-> <out_keys.bin> <out_vals.bin|->
-//        ref_cub_radix_sort bench <ktype> <vbytes> <log2n> <desc> <begin_bit> <end_bit> <and_rounds> <iters>
+//        ref_cub_radix_sort bench <ktype> <vbytes> <log2n> <desc> <begin_bit> <end_bit> <dist> <iters>
+//          dist: a number R = bitwise AND of R uniform words (1 = uniform, 3 = bit entropy 0.544, 5 = 0.201; as
+//          cub/benchmarks/nvbench_helper.cu:370-400), or equal | fewK (K distinct keys, e.g. few16) | sorted
+//          log2n may also be a plain item count written as n=<items>
 //        ref_cub_radix_sort segsort <ktype> <vbytes> <n> <desc> <begin_bit> <end_bit> <keys.bin> <vals.bin|-> <out_keys.bin> <out_vals.bin|-> <num_segments> <begin_offsets.bin> <end_offsets.bin>
 //          (cub::DeviceSegmentedRadixSort; offsets are int64; the output buffers are pre-filled with the input so that
 //           positions outside every segment are defined)
@@ -178,22 +181,47 @@ int run(int argc, char** argv, bool pairs)
     return 0;
   }
   // bench
-  const size_t n       = size_t(1) << atoi(argv[4]);
-  const int and_rounds = atoi(argv[8]);
-  const int iters      = atoi(argv[9]);
-  std::vector<K> hk(n);
+  const size_t n = strncmp(argv[4], "n=", 2) == 0 ? strtoull(argv[4] + 2, nullptr, 10) : size_t(1) << atoi(argv[4]);
+  const std::string dist = argv[8];
+  const bool numeric     = !dist.empty() && dist[0] >= '0' && dist[0] <= '9';
+  const int and_rounds   = numeric ? atoi(argv[8]) : 1;
+  const int iters        = atoi(argv[9]);
+  std::vector<K> hk(n + 8 / sizeof(K));
   {
     std::mt19937_64 rng(42);
     uint64_t* w  = reinterpret_cast<uint64_t*>(hk.data());
-    size_t words = n * sizeof(K) / 8;
-    for (size_t i = 0; i < words; ++i)
+    size_t words = (n * sizeof(K) + 7) / 8;
+    if (dist == "equal")
     {
-      uint64_t x = rng();
-      for (int r = 1; r < and_rounds; ++r)
+      for (size_t i = 0; i < words; ++i)
       {
-        x &= rng();
+        w[i] = 0x0123456701234567ull;
       }
-      w[i] = x;
+    }
+    else if (dist.rfind("few", 0) == 0)
+    {
+      const int k = atoi(dist.c_str() + 3) > 0 ? atoi(dist.c_str() + 3) : 16;
+      std::vector<uint64_t> pool(k);
+      for (auto& x : pool)
+      {
+        x = rng();
+      }
+      for (size_t i = 0; i < n; ++i)
+      {
+        memcpy(reinterpret_cast<char*>(hk.data()) + i * sizeof(K), &pool[rng() % k], sizeof(K));
+      }
+    }
+    else
+    {
+      for (size_t i = 0; i < words; ++i)
+      {
+        uint64_t x = rng();
+        for (int r = 1; r < and_rounds; ++r)
+        {
+          x &= rng();
+        }
+        w[i] = x;
+      }
     }
   }
   K *kin, *kout;
@@ -211,6 +239,17 @@ int run(int argc, char** argv, bool pairs)
   CK((do_sort<K, V>(nullptr, bytes, kin, kout, vin, vout, n, desc, b, e, pairs)));
   void* tmp;
   CK(cudaMalloc(&tmp, bytes));
+  if (dist == "sorted")
+  {
+    // the timed input is the already sorted array (in the requested order, all bits)
+    size_t sb = 0;
+    CK((do_sort<K, V>(nullptr, sb, kin, kout, vin, vout, n, desc, 0, int(sizeof(K) * 8), false)));
+    void* st;
+    CK(cudaMalloc(&st, sb));
+    CK((do_sort<K, V>(st, sb, kin, kout, vin, vout, n, desc, 0, int(sizeof(K) * 8), false)));
+    CK(cudaMemcpy(kin, kout, n * sizeof(K), cudaMemcpyDeviceToDevice));
+    CK(cudaFree(st));
+  }
   for (int i = 0; i < 3; ++i)
   {
     CK((do_sort<K, V>(tmp, bytes, kin, kout, vin, vout, n, desc, b, e, pairs)));
@@ -230,8 +269,8 @@ int run(int argc, char** argv, bool pairs)
   CK(cudaEventElapsedTime(&ms, e0, e1));
   ms /= iters;
   printf("{\"impl\": \"cub-3.6.0 (reference, same GPU)\", \"ktype\": \"%s\", \"vbytes\": %d, \"n\": %zu, \"desc\": %d, "
-         "\"begin_bit\": %d, \"end_bit\": %d, \"and_rounds\": %d, \"ms\": %.4f, \"gkeys_s\": %.3f, \"temp_bytes\": %zu}\n",
-         argv[2], pairs ? int(sizeof(V)) : 0, n, int(desc), b, e, and_rounds, ms, n / ms / 1e6, bytes);
+         "\"begin_bit\": %d, \"end_bit\": %d, \"dist\": \"%s\", \"ms\": %.4f, \"gkeys_s\": %.3f, \"temp_bytes\": %zu}\n",
+         argv[2], pairs ? int(sizeof(V)) : 0, n, int(desc), b, e, dist.c_str(), ms, n / ms / 1e6, bytes);
   return 0;
 }
 
