@@ -141,10 +141,12 @@ def cpu_reference_run(steps, warmup, log2n=24, threads=None, pairs=False):
     if lib is None:
         kind = "port"
     if lib is not None:
-        cores = lib.ref_thrust_max_threads()
-        if threads:
-            lib.ref_thrust_set_threads(threads)
-            cores = threads
+        # all the host cores this process may use: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would silently
+        # turn the N > 1 reference arm into a one-core run
+        if not threads:
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        lib.ref_thrust_set_threads(threads)
+        cores = threads
         times = []
         for i in range(warmup + steps):
             secs = ref_thrust_sort(keys, vals, backend="omp")[-1]

@@ -262,6 +262,18 @@ class CudaOps:
         self.kernel_launches += 1
         return True
 
+    def partition_to_peers_supported(self, key_dtype, value_bytes):
+        """True when the library has a bucket-mode kernel for these widths (a property of the types alone, so every
+        rank answers alike)."""
+        import ctypes
+
+        kdt = np.dtype(key_dtype)
+        one = (ctypes.c_uint64 * 1)(0)
+        nbytes = ctypes.c_size_t(0)
+        rc = self.lib.b200rs_partition_to_peers(None, ctypes.byref(nbytes), None, None, 1, key_kind_of(kdt),
+                                                kdt.itemsize, int(value_bytes), 0, one, 0, one, 1, one, one, one, None)
+        return rc == 0
+
     def partition(self, ids, nbits, keys, values):
         """Stable partition of (keys, values) by the bucket id of each item: one radix pass over the low `nbits` bits
         of the 1-byte ids with the payload as the value (b200rs_sort, pointer form)."""
@@ -578,30 +590,38 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
     if protocol == "partition":
         # 2 + 3 fused: ONE kernel partitions by destination and stores every item straight into the receive buffer of
         # its destination GPU (peer-mapped symmetric memory) -- the compute step and the collective that follows it
-        if use_peer and exchange != "peer" and int(n_all.max()) > 0 and hasattr(ops, "partition_to_peers"):
+        # Eligibility is decided from GLOBALLY known facts only (the largest shard, the key / value widths), so that
+        # every rank takes the same path: the code below contains cross-GPU barriers.
+        es_k = keys.element_size()
+        es_v = values.element_size() if values is not None else 0
+        fused_ok = (use_peer and exchange != "peer" and 0 < int(n_all.max()) < (1 << 30)
+                    and hasattr(ops, "partition_to_peers") and ops.partition_to_peers_supported(kdt, es_v))
+        pb = None
+        if fused_ok:
             try:
-                es_k = keys.element_size()
-                es_v = values.element_size() if values is not None else 0
                 pb = _PeerBuffers.get(int(n_all.max()) * max(es_k, es_v), keys.device, group, dist)
-                counts = edges[:, 1:] - edges[:, :-1]
-                dst_off = np.cumsum(counts, axis=0) - counts
-                bias = dst_off[rank] - edges[rank, :-1]  # destination index of partitioned index 0, per rank
-                dst_k = [pb.ptrs[0][r] + int(bias[r]) * es_k for r in range(world)]
-                dst_v = [pb.ptrs[1][r] + int(bias[r]) * es_v for r in range(world)]
-                pb.hdls[0].barrier(channel=0)  # every peer has finished reading its receive buffers
-                fused_done = ops.partition_to_peers(keys, values, splitters, sizes, descending,
-                                                    edges[rank, 1:-1].tolist(), dst_k, dst_v)
-                pb.hdls[0].barrier(channel=1)  # every source's stores have landed (needed after the first one, too)
-                if fused_done:
-                    rkeys = pb.bufs[0][: n_local * es_k].view(keys.dtype)
-                    rvals = pb.bufs[1][: n_local * es_v].view(values.dtype) if values is not None else None
-                    peer_done = True
-                    ph.mark("partition")
-            except (RuntimeError, ImportError, AttributeError) as ex:  # symmetric memory not available
+            except (RuntimeError, ImportError, AttributeError) as ex:  # symmetric memory not available (every rank alike)
                 if exchange == "fused":
                     raise
                 if stats is not None:
                     stats["peer_exchange_unavailable"] = repr(ex)
+        if pb is not None:
+            counts = edges[:, 1:] - edges[:, :-1]
+            dst_off = np.cumsum(counts, axis=0) - counts
+            bias = dst_off[rank] - edges[rank, :-1]  # destination index of partitioned index 0, per rank
+            dst_k = [pb.ptrs[0][r] + int(bias[r]) * es_k for r in range(world)]
+            dst_v = [pb.ptrs[1][r] + int(bias[r]) * es_v for r in range(world)]
+            # no exception is swallowed between the two barriers: a rank that fails here fails the job
+            pb.hdls[0].barrier(channel=0)  # every peer has finished reading its receive buffers
+            ok_ = ops.partition_to_peers(keys, values, splitters, sizes, descending, edges[rank, 1:-1].tolist(), dst_k,
+                                         dst_v)
+            pb.hdls[0].barrier(channel=1)  # every source's stores have landed (needed after the first one, too)
+            if not ok_:
+                raise RuntimeError("b200rs_partition_to_peers refused a problem the size query accepted")
+            fused_done = peer_done = True
+            rkeys = pb.bufs[0][: n_local * es_k].view(keys.dtype)
+            rvals = pb.bufs[1][: n_local * es_v].view(values.dtype) if values is not None else None
+            ph.mark("partition")
         if not fused_done:
             fused = getattr(ops, "partition_by_splitters", None)
             part = fused(keys, values, splitters, sizes, descending) if fused is not None else None

@@ -128,16 +128,58 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
     e2e_ms = float(e2e_ms.item())
     ok, ov = distributed_sort(keys, vals, out=out_buf)  # keys/vals still hold the shard (uploaded from h_keys/h_vals)
 
-    # sortedness + conservation spot checks on the last result (full parity lives in tests/)
-    s = ok.view(torch.int32).view(torch.uint8).view(-1, 4)  # noqa: F841  (kept on device; check order below)
+    # ---- verification of the last result, on the device, at every N (asserts; the line carries "verified": true).
+    # Mirrors /root/reference/cudax/test/multi_gpu/algorithms/sort/sort_common.cuh:128-155 (global order of the
+    # concatenated per-rank outputs) and adds what a STABLE pair sort must also satisfy.  Values are the global input
+    # positions (rank * n + i), so: (1) every rank's output is ordered by key; (2) inside a run of equal keys the
+    # values increase (stability: earlier rank, then earlier local position, first); (3) the same two properties hold
+    # across every rank boundary; (4) pairing: the key stored at global input position vals_out[j] is keys_out[j]
+    # (every source rank's shard is regenerated from its seed); (5) the multiset of values is exactly 0 .. total-1
+    # (sum and sum of squares modulo 2^64, counts per rank).
+    total = n * world
     k64 = ok.to(torch.int64)
+    v64 = ov.to(torch.int64)
+    assert ok.numel() == n and ov.numel() == n, "bench: per-rank output count differs from the input count"
     assert bool((k64[1:] >= k64[:-1]).all()), "bench: local output not sorted"
-    edge = torch.stack([k64[0], k64[-1]])
+    ties = k64[1:] == k64[:-1]
+    assert bool((v64[1:][ties] > v64[:-1][ties]).all()), "bench: equal keys are not in input order (stability)"
+    edge = torch.stack([k64[0], v64[0], k64[-1], v64[-1]])
     edges = [torch.empty_like(edge) for _ in range(world)]
     dist.all_gather(edges, edge)
-    if rank == 0:
-        for a, b in zip(edges[:-1], edges[1:]):
-            assert int(a[1]) <= int(b[0]), "bench: ranks are not globally ordered"
+    for a, b in zip(edges[:-1], edges[1:]):
+        la, fb = (int(a[2]), int(a[3])), (int(b[0]), int(b[1]))
+        assert la < fb, "bench: ranks are not globally ordered / stable across a rank boundary"
+    src_of = v64 // n
+    for src in range(world):
+        gs = torch.Generator(device="cuda").manual_seed(42 + src)
+        ks = torch.randint(-(2**31), 2**31 - 1, (n,), dtype=torch.int32, device="cuda", generator=gs)
+        m = src_of == src
+        assert bool((ks[(v64[m] - src * n)] == ok.view(torch.int32)[m]).all()), "bench: key/value pairing broken"
+        del ks, m
+    sums = torch.stack([v64.sum(), (v64 * v64).sum()])  # int64 arithmetic wraps modulo 2^64
+    dist.all_reduce(sums)
+    want1 = (total * (total - 1) // 2) % (1 << 64)
+    want2 = ((total - 1) * total * (2 * total - 1) // 6) % (1 << 64)
+    got1, got2 = int(sums[0]) % (1 << 64), int(sums[1]) % (1 << 64)
+    assert (got1, got2) == (want1, want2), "bench: the output values are not a permutation of the input positions"
+    verified = True
+    del k64, v64, src_of, ties
+
+    # ---- like-for-like anchor: the local (u32, u32) sort of one shard on this GPU, in the same run (every rank runs it
+    # at the same time, rank 0 reports): efficiency_like_for_like = per-GPU throughput of the job / this
+    from .multi_gpu import _default_ops as _ops
+
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        _ops().sort_pairs(keys, vals, False, preserve_input=True, out=out_buf)
+    a0.record()
+    for _ in range(5):
+        _ops().sort_pairs(keys, vals, False, preserve_input=True, out=out_buf)
+    a1.record()
+    torch.cuda.synchronize()
+    anchor_ms = a0.elapsed_time(a1) / 5
+    barrier()
 
     phase_ms = {k: sum(v) / len(v) for k, v in phase.items()}
     PH = ("splitters", "partition", "exchange", "final_sort", "local_sort")
@@ -147,7 +189,6 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
     dist.all_reduce(xbytes, op=dist.ReduceOp.MAX)
     if rank == 0:
         peak, peak_src = measured_peaks()
-        total = n * world
         fused = st.get("exchange") == "fused"
         ex_ms = float(ph[1]) if fused else float(ph[2])  # fused: the partition kernel IS the exchange
         one = 2.0 * n * 8  # bytes one onesweep pass moves per GPU
@@ -186,6 +227,12 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
             "exchange": {"fused_with_partition_pass": fused, "bytes_out_per_gpu": float(xbytes), "ms": ex_ms,
                          "GBps_per_direction": float(xbytes) / (ex_ms * 1e-3) / 1e9 if ex_ms > 0 else None,
                          "nvlink_peak_GBps": 770.0, "peak_source": "measured peer copy (B200_PROFILING.md)"},
+            "verified": verified,
+            "verification": "on device, every rank: order, stability inside equal-key runs and across rank boundaries, "
+                            "pairing keys_in[vals_out] == keys_out, values are a permutation of the input positions",
+            "scale_anchor": {"workload": "local SortPairs of one shard (u32, u32), same run, rank 0",
+                             "ms_per_step": anchor_ms, "value": n / (anchor_ms * 1e-3) / 1e9, "unit": "Gkeys/s"},
+            "efficiency_like_for_like": (total / (ms * 1e-3) / 1e9) / (world * n / (anchor_ms * 1e-3) / 1e9),
             "cpu_baseline": None,
             "e2e": {"value": total / (e2e_ms * 1e-3) / 1e9, "unit": "Gkeys/s", "h2d_bytes_per_step": n * 8 * world,
                     "d2h_bytes_per_step": n * 8 * world, "ms_per_step": e2e_ms, "steps": e2e_steps,
