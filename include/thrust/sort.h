@@ -13,7 +13,15 @@
 
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <type_traits>
+
+#if defined(__has_include)
+#  if __has_include(<cuda/std/functional>)
+#    include <cuda/std/functional>
+#    define B200RS_THRUST_SHIM_HAS_CUDA_STD 1
+#  endif
+#endif
 
 #include "../b200rs.h"
 #include "device_vector.h"
@@ -68,12 +76,40 @@ T* unwrap(T* it)
 {
   return it;
 }
+// Comparators the radix-sort path accepts (reference: __smart_sort::can_use_primitive_sort, sort.h:288-301): the
+// less / greater function objects of thrust, std and cuda::std.  0 = not a radix comparator, 1 = ascending,
+// 2 = descending.  Anything else would need the reference's merge sort, which this path does not have: it is a compile
+// error here, never a silent ascending sort.
 template <class C>
-struct is_descending : std::false_type
+struct radix_order : std::integral_constant<int, 0>
 {};
 template <class T>
-struct is_descending<greater<T>> : std::true_type
+struct radix_order<less<T>> : std::integral_constant<int, 1>
 {};
+template <class T>
+struct radix_order<greater<T>> : std::integral_constant<int, 2>
+{};
+template <class T>
+struct radix_order<std::less<T>> : std::integral_constant<int, 1>
+{};
+template <class T>
+struct radix_order<std::greater<T>> : std::integral_constant<int, 2>
+{};
+#ifdef B200RS_THRUST_SHIM_HAS_CUDA_STD
+template <class T>
+struct radix_order<::cuda::std::less<T>> : std::integral_constant<int, 1>
+{};
+template <class T>
+struct radix_order<::cuda::std::greater<T>> : std::integral_constant<int, 2>
+{};
+#endif
+template <class C>
+struct is_descending : std::integral_constant<bool, radix_order<C>::value == 2>
+{
+  static_assert(radix_order<C>::value != 0,
+                "thrust::sort shim: only less<T> / greater<T> (thrust, std or cuda::std) select the radix-sort path; "
+                "other comparators need the reference's merge sort");
+};
 
 template <class KeyIt, class Compare>
 void radix_sort_keys(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Compare)

@@ -41,6 +41,26 @@ def test_shim_programs_link_against_the_product_library():
         assert "libb200rs.so" in out
 
 
+def test_thrust_shim_rejects_non_radix_comparators(tmp_path):
+    """A comparator that is not less/greater (thrust, std, cuda::std) must not compile: the reference would run its
+    merge sort (thrust/system/cuda/detail/sort.h:288-339), this path has none and must not sort ascending silently."""
+    nvcc = "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    body = """#include <thrust/sort.h>
+template <class T> struct by_abs { bool operator()(T a, T b) const { return (a < 0 ? -a : a) < (b < 0 ? -b : b); } };
+int main() { int* d = nullptr; thrust::sort(d, d, %s); return 0; }
+"""
+    for comp, ok in (("thrust::greater<int>()", True), ("std::greater<int>()", True), ("by_abs<int>()", False)):
+        src = tmp_path / "t.cu"
+        src.write_text(body % comp)
+        res = subprocess.run([nvcc, "-std=c++17", "-arch=sm_100a", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
+                              str(tmp_path / "t.o")], capture_output=True, text=True, timeout=300)
+        assert (res.returncode == 0) == ok, (comp, res.stderr[-1500:])
+        if not ok:
+            assert "merge sort" in res.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("prog", ["test_cub_shim", "test_thrust_shim"])
 def test_shim_program_passes_on_gpu(prog):

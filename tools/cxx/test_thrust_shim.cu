@@ -84,6 +84,16 @@ int main()
     ASSERT_TRUE((v.to_host() == std::vector<int>{0, 1, 2, 3, 4, 5, 6}));
     thrust::sort(v.begin(), v.end(), thrust::greater<int>());
     ASSERT_TRUE((v.to_host() == std::vector<int>{6, 5, 4, 3, 2, 1, 0}));
+    // the std / cuda::std function objects select the same radix path (sort.h:288-301); any other comparator is a
+    // compile error in this shim (checked by tests/test_cxx_shims.py), never a silent ascending sort
+    thrust::sort(v.begin(), v.end(), std::less<int>());
+    ASSERT_TRUE((v.to_host() == std::vector<int>{0, 1, 2, 3, 4, 5, 6}));
+    thrust::sort(v.begin(), v.end(), std::greater<int>());
+    ASSERT_TRUE((v.to_host() == std::vector<int>{6, 5, 4, 3, 2, 1, 0}));
+    thrust::stable_sort(v.begin(), v.end(), ::cuda::std::less<int>());
+    ASSERT_TRUE((v.to_host() == std::vector<int>{0, 1, 2, 3, 4, 5, 6}));
+    thrust::stable_sort(v.begin(), v.end(), ::cuda::std::greater<int>());
+    ASSERT_TRUE((v.to_host() == std::vector<int>{6, 5, 4, 3, 2, 1, 0}));
   }
   { // TestSortByKeySimple (thrust/testing/sort_by_key.cu:46-53)
     thrust::device_vector<int> k(std::vector<int>{1, 3, 6, 5, 2, 0, 4});
