@@ -23,6 +23,11 @@ EXPORTS = (
     "b200rs_bucket_ids",
     "b200rs_partition_by_splitters",
     "b200rs_partition_to_peers",
+    "b200rs_multi_comm_create",
+    "b200rs_multi_comm_destroy",
+    "b200rs_multi_status",
+    "b200rs_multi_last_launch_count",
+    "b200rs_sort_multi",
     "b200rs_last_launch_count",
     "b200rs_set_config",
     "b200rs_set_portion_items",
@@ -32,6 +37,9 @@ EXPORTS = (
     "b200rs_timing_enable",
     "b200rs_timing_read",
 )
+
+# b200rs_allgather_fn: int (*)(void* ctx, const void* send, void* recv, size_t bytes_per_rank)
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 
 _lib = None
 
@@ -75,6 +83,16 @@ def lib() -> ctypes.CDLL:
         l.b200rs_partition_to_peers.restype = i32
         l.b200rs_partition_to_peers.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, u64, i32, i32, i32, i32,
                                                 pu64, i32, pu64, i32, pu64, pu64, pu64, vp]
+        l.b200rs_multi_comm_create.restype = i32
+        l.b200rs_multi_comm_create.argtypes = [ctypes.POINTER(vp), i32, i32, ctypes.c_size_t, ALLGATHER_FN, vp]
+        l.b200rs_multi_comm_destroy.restype = i32
+        l.b200rs_multi_comm_destroy.argtypes = [vp]
+        l.b200rs_multi_status.restype = i32
+        l.b200rs_multi_status.argtypes = [vp, ctypes.POINTER(i32)]
+        l.b200rs_multi_last_launch_count.restype = i32
+        l.b200rs_multi_last_launch_count.argtypes = [vp]
+        l.b200rs_sort_multi.restype = i32
+        l.b200rs_sort_multi.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, vp, vp, u64, i32, i32, i32, i32, vp]
         l.b200rs_last_launch_count.restype = i32
         l.b200rs_last_launch_count.argtypes = []
         l.b200rs_set_config.restype = i32

@@ -222,6 +222,17 @@ struct PeerTable
   uint32_t seg_end[16]; // seg_end[r] = first partitioned index that does NOT go to ranks <= r
 };
 
+// Bucket mode driven from the device (multi-GPU sort, multi.cu): the kernel that ends the splitter selection writes the
+// plan, the partition pass that follows it in the stream reads it -- no host round trip in between.
+struct PartitionPlan
+{
+  uint32_t num_splitters;
+  uint32_t status;                      // 0 = consistent; else MULTI_ERR_* bits (multi.cu)
+  unsigned long long splitters[16];     // bit-ordered, strictly increasing
+  unsigned long long bins[256];         // exclusive output offset of every bucket (PassArgs::bins points here)
+  PeerTable peer;                       // PassArgs::peer points here
+};
+
 // Everything one digit pass over one portion needs (type-erased; kernels cast).
 struct PassArgs
 {
@@ -249,6 +260,7 @@ struct PassArgs
   int num_splitters;
   unsigned long long splitters[15];
   const PeerTable* peer; // bucket mode: remote destinations (device memory), or nullptr for keys_out / vals_out
+  const PartitionPlan* plan; // bucket mode: splitters come from this device-side plan instead of the fields above
   int sm_count;          // SMs of the current device (grid size of the persistent kernel)
 };
 

@@ -598,6 +598,7 @@ int b200rs_sort(
       a.xf           = xf;
       a.num_splitters = 0;
       a.peer          = nullptr;
+      a.plan          = nullptr;
       a.sm_count      = sms;
       mark_op(stream, OP_ONESWEEP);
       e = cfg->launch(a, tiles, stream);
@@ -641,7 +642,8 @@ static int partition_impl(
   const uint64_t* h_segment_ends,
   const uint64_t* h_rank_dst_keys,
   const uint64_t* h_rank_dst_vals,
-  b200rs_stream_t stream_)
+  b200rs_stream_t stream_,
+  const PartitionPlan* d_plan = nullptr) // device-side plan (multi.cu): replaces every h_* argument
 {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   t_last_launches     = 0;
@@ -693,7 +695,14 @@ static int partition_impl(
     return 0;
   }
   const bool remote = num_dests > 0;
-  if (d_keys_in == nullptr || (value_bytes > 0 && d_values_in == nullptr) || (num_splitters > 0 && h_splitters == nullptr)
+  if (d_plan != nullptr)
+  {
+    if (d_keys_in == nullptr || (value_bytes > 0 && d_values_in == nullptr) || !remote)
+    {
+      return int(cudaErrorInvalidValue);
+    }
+  }
+  else if (d_keys_in == nullptr || (value_bytes > 0 && d_values_in == nullptr) || (num_splitters > 0 && h_splitters == nullptr)
       || h_bucket_offsets == nullptr
       || (!remote && (d_keys_out == nullptr || (value_bytes > 0 && d_values_out == nullptr)))
       || (remote && (h_rank_dst_keys == nullptr || (value_bytes > 0 && h_rank_dst_vals == nullptr)
@@ -713,7 +722,7 @@ static int partition_impl(
   {
     return int(e);
   }
-  if (remote)
+  if (remote && d_plan == nullptr)
   {
     // which rank each bucket goes to (0 = a segment boundary falls inside it: resolved per item in the kernel)
     PeerTable pt;
@@ -747,11 +756,14 @@ static int partition_impl(
     }
   }
   // exclusive bucket offsets (2 * num_splitters + 1 of them) -> the pass's per-digit output offsets
-  e = cudaMemcpyAsync(base + off_bins, h_bucket_offsets, size_t(2 * num_splitters + 1) * sizeof(uint64_t),
-                      cudaMemcpyHostToDevice, stream);
-  if (e != cudaSuccess)
+  if (d_plan == nullptr)
   {
-    return int(e);
+    e = cudaMemcpyAsync(base + off_bins, h_bucket_offsets, size_t(2 * num_splitters + 1) * sizeof(uint64_t),
+                        cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess)
+    {
+      return int(e);
+    }
   }
   PassArgs a;
   a.keys_in             = d_keys_in;
@@ -762,7 +774,7 @@ static int partition_impl(
   a.lookback_next       = nullptr;
   a.lookback_next_tiles = 0;
   a.tile_counter        = reinterpret_cast<uint32_t*>(base + off_ctr);
-  a.bins                = reinterpret_cast<unsigned long long*>(base + off_bins);
+  a.bins                = d_plan != nullptr ? d_plan->bins : reinterpret_cast<unsigned long long*>(base + off_bins);
   a.bins_next           = nullptr;
   a.num_items           = uint32_t(num_items);
   a.num_tiles           = unsigned(tiles);
@@ -773,18 +785,33 @@ static int partition_impl(
   a.last_pass           = 1;
   a.big                 = 0;
   a.xf                  = make_xform(key_kind, key_bytes, descending);
-  a.num_splitters       = num_splitters;
-  for (int i = 0; i < num_splitters; ++i)
+  a.num_splitters       = d_plan != nullptr ? 0 : num_splitters;
+  for (int i = 0; i < num_splitters && d_plan == nullptr; ++i)
   {
     a.splitters[i] = h_splitters[i];
   }
-  a.peer     = remote ? reinterpret_cast<const PeerTable*>(base + off_peer) : nullptr;
+  a.peer     = d_plan != nullptr ? &d_plan->peer
+                                 : (remote ? reinterpret_cast<const PeerTable*>(base + off_peer) : nullptr);
+  a.plan     = d_plan;
   a.sm_count = sms;
   mark_op(stream, OP_ONESWEEP);
   e = cfg->launch_bucket(a, unsigned(tiles), stream);
   mark_end(stream);
   return int(e);
 }
+
+namespace b200rs
+{
+// multi.cu: the fused partition + exchange pass driven by a PartitionPlan in device memory
+int partition_with_plan(void* d_temp_storage, size_t* temp_storage_bytes, const void* d_keys_in, const void* d_values_in,
+                        uint64_t num_items, int key_kind, int key_bytes, int value_bytes, int descending, int num_dests,
+                        const PartitionPlan* d_plan, cudaStream_t stream)
+{
+  return partition_impl(d_temp_storage, temp_storage_bytes, d_keys_in, nullptr, d_values_in, nullptr, num_items, key_kind,
+                        key_bytes, value_bytes, descending, nullptr, 0, nullptr, num_dests, nullptr, nullptr, nullptr,
+                        reinterpret_cast<b200rs_stream_t>(stream), d_plan);
+}
+} // namespace b200rs
 
 extern "C" {
 

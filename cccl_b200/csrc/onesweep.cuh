@@ -73,7 +73,8 @@ struct OnesweepSmem
   static constexpr uint32_t OFF_END  = OFF_GOFF + RADIX * 8;          // u32 [256] end of each digit's staged run
                                                                       // (bucket mode only, else empty)
   static constexpr uint32_t OFF_PEER = OFF_END + ((OPT & 8) ? RADIX * 4 : 0); // PeerTable copy (bucket mode only)
-  static constexpr uint32_t OFF_MISC = OFF_PEER + ((OPT & 8) ? uint32_t((sizeof(PeerTable) + 15) / 16 * 16) : 0u); // u32 [16]
+  static constexpr uint32_t OFF_SPLIT = OFF_PEER + ((OPT & 8) ? uint32_t((sizeof(PeerTable) + 15) / 16 * 16) : 0u); // u64 [16] splitters + u32 count (bucket mode only)
+  static constexpr uint32_t OFF_MISC = OFF_SPLIT + ((OPT & 8) ? 16u * 8u + 16u : 0u); // u32 [16]
   static constexpr uint32_t OFF_DATA = OFF_MISC + 64;                 // staged tile (16-byte aligned)
   static constexpr size_t BYTES      = size_t(OFF_DATA) + size_t(TILE) * ITEM_BYTES;
 };
@@ -239,27 +240,47 @@ __device__ __forceinline__ uint32_t pass_digit(U key, int shift, uint32_t mask, 
   return uint32_t(key >> shift) & mask;
 }
 
-// The digit of one key for this launch: bits [shift, shift + 8) of the bit-ordered key, or (bucket mode) the key's
-// destination bucket against the splitters.  Monotone in the key, so the all-ones padding key gets the largest digit.
+// The digit of one key for this launch: bits [shift, shift + 8) of the bit-ordered key.  (Bucket mode -- the key's
+// destination bucket against the splitters -- is evaluated once per tile, splitter-major, by bucket_ids_of_tile.)
 template <bool FLOATK, bool BUCKET, class U>
 __device__ __forceinline__ uint32_t tile_digit(const PassArgs& a, U key, int shift, uint32_t mask, U neg_zero, U pos_zero)
 {
-  if (BUCKET)
-  {
-    if (FLOATK)
-    {
-      key = key == neg_zero ? pos_zero : key;
-    }
-    uint32_t id = 0;
-#pragma unroll 1
-    for (int j = 0; j < a.num_splitters; ++j)
-    {
-      const U s = U(a.splitters[j]);
-      id += (key > s ? 1u : 0u) + (key >= s ? 1u : 0u);
-    }
-    return id;
-  }
+  static_assert(!BUCKET, "bucket ids come from bucket_ids_of_tile");
   return pass_digit<FLOATK>(key, shift, mask, neg_zero, pos_zero);
+}
+
+// Bucket mode: id = 2 * #{splitters below the key} + [key equals a splitter], for every key of the thread, packed four
+// ids per register.  Splitter-major: each splitter is read ONCE per thread (a broadcast shared-memory load from the
+// table the kernel prologue filled from the kernel arguments or from a device-side PartitionPlan), then compared with
+// all IPT keys.  Monotone in the key, so the all-ones padding key gets the largest id.
+template <bool FLOATK, int IPT, class U>
+__device__ __forceinline__ void
+bucket_ids_of_tile(uint32_t s_split, const U (&key)[IPT], U neg_zero, U pos_zero, uint32_t (&bid)[(IPT + 3) / 4])
+{
+#pragma unroll
+  for (int q = 0; q < (IPT + 3) / 4; ++q)
+  {
+    bid[q] = 0;
+  }
+  uint32_t ns;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ns) : "r"(s_split + 128u));
+#pragma unroll 1
+  for (uint32_t j = 0; j < ns; ++j)
+  {
+    unsigned long long s64;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(s64) : "r"(s_split + j * 8u));
+    const U s = U(s64);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+      U k = key[i];
+      if (FLOATK)
+      {
+        k = k == neg_zero ? pos_zero : k;
+      }
+      bid[i / 4] += ((k > s ? 1u : 0u) + (k >= s ? 1u : 0u)) << (8 * (i & 3));
+    }
+  }
 }
 
 // Bucket mode with remote destinations: byte address of the item with partitioned index idx and bucket d.
@@ -560,7 +581,7 @@ __device__ __forceinline__ void onesweep_tile(
   // costs the normal path one shuffle, one compare and one vote per warp and tile (the full check only runs when the
   // first row already agrees).
   bool warp_single = false;
-  if ((OPT & OPT_SHORT_WARP) && !BUCKET)
+  if constexpr ((OPT & OPT_SHORT_WARP) != 0 && !BUCKET)
   {
     const uint32_t d0    = tile_digit<FLOATK, BUCKET>(a, key[0], shift, dmask, neg_zero, pos_zero);
     const uint32_t first = __shfl_sync(0xffffffffu, d0, 0);
@@ -587,6 +608,10 @@ __device__ __forceinline__ void onesweep_tile(
       }
     }
   }
+  if constexpr (BUCKET)
+  {
+    bucket_ids_of_tile<FLOATK, IPT>(sbase + L::OFF_SPLIT, key, neg_zero, pos_zero, bid);
+  }
   if (!warp_single)
   {
 #pragma unroll
@@ -601,7 +626,14 @@ __device__ __forceinline__ void onesweep_tile(
     }
     else
     {
-      d   = tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
+      if constexpr (BUCKET)
+      {
+        d = (bid[i / 4] >> (8 * (i & 3))) & 0xffu;
+      }
+      else
+      {
+        d = tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
+      }
       ctr = s_mine + d * CB;
       if (RANK == RANK_MATCH)
       {
@@ -625,11 +657,6 @@ __device__ __forceinline__ void onesweep_tile(
       ctr_st<C16>(ctr, next);
     }
     put16(rank2, i, next);
-    if (BUCKET)
-    {
-      // the bucket of a key costs a loop over the splitters: keep it (8 bits) instead of evaluating it again
-      bid[i / 4] = (i & 3) == 0 ? d : (bid[i / 4] | (d << (8 * (i & 3))));
-    }
   }
   }
   after_rank();
@@ -706,9 +733,16 @@ __device__ __forceinline__ void onesweep_tile(
       }
       else
       {
-        const uint32_t d = BUCKET ? ((bid[i / 4] >> (8 * (i & 3))) & 0xffu)
-                                  : tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
-        centry           = s_mine + d * CB;
+        uint32_t d;
+        if constexpr (BUCKET)
+        {
+          d = (bid[i / 4] >> (8 * (i & 3))) & 0xffu;
+        }
+        else
+        {
+          d = tile_digit<FLOATK, BUCKET>(a, key[i], shift, dmask, neg_zero, pos_zero);
+        }
+        centry = s_mine + d * CB;
       }
       const uint32_t r = get16(rank2, i) + ctr_ld<C16>(centry);
       if (VBYTES > 0)
@@ -862,7 +896,7 @@ __device__ __forceinline__ void onesweep_tile(
         {
           // nothing: the offset entry is addressed straight from the key below
         }
-        else
+        else if constexpr (!BUCKET)
         {
           d = tile_digit<FLOATK, BUCKET>(a, k, shift, dmask, neg_zero, pos_zero);
         }
@@ -975,6 +1009,11 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
   const uint32_t sbase = uint32_t(__cvta_generic_to_shared(smem));
   const uint32_t tid   = threadIdx.x;
 
+  if ((OPT & OPT_BUCKET) && a.plan != nullptr && a.plan->status != 0)
+  {
+    return; // the device-side plan is flagged inconsistent / over capacity (multi.cu): store nothing anywhere
+  }
+
   // ---- dynamic tile id: a tile only starts after all its predecessors started (look-back cannot deadlock)
   if (tid == 0)
   {
@@ -990,6 +1029,20 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
       sts32(sbase + L::OFF_WARP + (j * NT + tid) * 4, 0);
     }
     static_assert(WORDS % NT == 0, "counter words must divide evenly over the threads");
+  }
+  if (OPT & OPT_BUCKET)
+  {
+    // splitters: from the kernel arguments, or from a PartitionPlan a kernel earlier in the stream wrote (multi-GPU
+    // sort: the host never sees the splitters)
+    if (tid < 16)
+    {
+      const unsigned long long v = a.plan != nullptr ? a.plan->splitters[tid] : (tid < 15 ? a.splitters[tid] : 0ull);
+      sts64(sbase + L::OFF_SPLIT + tid * 8, v);
+    }
+    if (tid == 16)
+    {
+      sts32(sbase + L::OFF_SPLIT + 128, a.plan != nullptr ? a.plan->num_splitters : uint32_t(a.num_splitters));
+    }
   }
   if ((OPT & OPT_BUCKET) && a.peer != nullptr)
   {

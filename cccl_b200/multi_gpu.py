@@ -514,6 +514,100 @@ def _byte_view():
     return torch.uint8
 
 
+class NativeComm:
+    """The C++ multi-GPU sort (b200rs_multi_comm_* / b200rs_sort_multi, cccl_b200/csrc/multi.cu): after the collective
+    creation (CUDA IPC handles all-gathered through torch.distributed, any backend) a sort is one C-ABI call that
+    enqueues kernels only -- no NCCL call, no host wait.  One communicator per (group, device), grown (collectively) when
+    a larger receive buffer is needed."""
+
+    _cache = {}
+
+    def __init__(self, receive_bytes, device, group, dist):
+        import ctypes
+
+        import torch
+
+        self.lib = _native.lib()
+        self.device, self.group = device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.receive_bytes = int(receive_bytes)
+        self.kernel_launches = 0
+        self._temp = None
+        on_gpu = dist.get_backend(group) == "nccl"
+
+        def allgather(_ctx, send, recv, nbytes):
+            try:
+                mine = torch.frombuffer(bytearray(ctypes.string_at(send, nbytes)), dtype=torch.uint8)
+                mine = mine.to(device) if on_gpu else mine
+                outs = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(outs, mine, group=group)
+                blob = b"".join(bytes(o.cpu().numpy().tobytes()) for o in outs)
+                ctypes.memmove(recv, blob, nbytes * self.world)
+                return 0
+            except Exception:  # noqa: BLE001  (reported to the C side as a failed all-gather)
+                return 1
+
+        self._cb = _native.ALLGATHER_FN(allgather)  # keep the callback object alive
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            rc = self.lib.b200rs_multi_comm_create(ctypes.byref(handle), self.rank, self.world, self.receive_bytes,
+                                                   self._cb, None)
+        _native.check(rc, "b200rs_multi_comm_create")
+        self.handle = handle
+
+    @classmethod
+    def get(cls, receive_bytes, device, group, dist):
+        key = (id(group), str(device))
+        cur = cls._cache.get(key)
+        if cur is None or cur.receive_bytes < receive_bytes:
+            if cur is not None:
+                cur.close()
+            cls._cache[key] = cur = cls(max(int(receive_bytes), 1 << 20), device, group, dist)
+        return cur
+
+    def close(self):
+        if self.handle:
+            self.lib.b200rs_multi_comm_destroy(self.handle)
+            self.handle = None
+
+    @staticmethod
+    def supported(key_bytes, value_bytes):
+        return key_bytes in (4, 8) and value_bytes in (0, 4, 8)
+
+    def sort(self, keys, values, descending, out=None):
+        import ctypes
+
+        import torch
+
+        kdt = _torch_np_dtype(keys)
+        n = keys.numel()
+        vb = values.element_size() if values is not None else 0
+        okeys = out[0] if out is not None else torch.empty_like(keys)
+        ovals = (out[1] if out is not None else torch.empty_like(values)) if values is not None else None
+        stream = torch.cuda.current_stream(keys.device).cuda_stream
+        p = lambda t: t.data_ptr() if t is not None and t.numel() else None
+        args = (n, key_kind_of(kdt), kdt.itemsize, vb, int(bool(descending)), stream)
+        nbytes = ctypes.c_size_t(0)
+        with torch.cuda.device(keys.device):
+            rc = self.lib.b200rs_sort_multi(self.handle, None, ctypes.byref(nbytes), None, None, None, None, *args)
+            _native.check(rc, "b200rs_sort_multi (size query)")
+            if self._temp is None or self._temp.numel() < nbytes.value:
+                self._temp = torch.empty(nbytes.value, dtype=torch.uint8, device=keys.device)
+            rc = self.lib.b200rs_sort_multi(self.handle, self._temp.data_ptr(), ctypes.byref(nbytes), p(keys), p(okeys),
+                                            p(values), p(ovals), *args)
+        _native.check(rc, "b200rs_sort_multi")
+        self.kernel_launches += self.lib.b200rs_multi_last_launch_count(self.handle)
+        return okeys, ovals
+
+    def status(self):
+        """Waits for the device; 0 = ok (see include/b200rs.h)."""
+        import ctypes
+
+        st = ctypes.c_int(0)
+        _native.check(self.lib.b200rs_multi_status(self.handle, ctypes.byref(st)), "b200rs_multi_status")
+        return st.value
+
+
 _DEFAULT_OPS = None
 
 
@@ -525,21 +619,50 @@ def _default_ops():
 
 
 def distributed_sort(keys, values=None, *, descending=False, group=None, ops=None, stats=None, protocol="partition",
-                     exchange="auto", out=None):
+                     exchange="auto", out=None, receive_items=None):
     """Stable distributed sort of one shard per rank; returns (keys_out, values_out) with len == len(keys).
     The caller's shard is left untouched.  ``stats`` (a dict) receives splitters, exchange counts and, on CUDA, the
     device time of each phase.  ``protocol``: "partition" (histogram select -> one partition pass -> exchange -> one
     sort) or "sort" (sort -> binary-search select -> exchange -> sort).  ``exchange``: "fused" (the partition kernel stores
     straight into the destination GPUs' receive buffers), "peer" (NVLink peer copies through symmetric memory),
-    "collective" (all-to-all-v) or "auto" (fused, else peer, on CUDA + NCCL; else collective).  ``out``: optional
+    "collective" (all-to-all-v) or "auto" (fused, else peer, on CUDA + NCCL; else collective).  ``protocol="native"``:
+    the same partition protocol with the host side in C++ (b200rs_sort_multi): no host wait, no NCCL call.  ``out``: optional
     (keys_out, values_out) tensors for the result (same length and dtype as the inputs)."""
     import torch
     import torch.distributed as dist
 
-    if protocol not in ("partition", "sort"):
+    if protocol not in ("partition", "sort", "native"):
         raise ValueError(f"unknown protocol {protocol!r}")
-    ops = ops or _default_ops()
     world = dist.get_world_size(group)
+    if protocol == "native":
+        # the C++ host path: one C-ABI call, kernels only.  `receive_items` (>= the largest shard of the job, the same
+        # number on every rank) sizes the receive buffers; a larger shard is reported through NativeComm.status() as a
+        # capacity error, nothing is written out of bounds
+        kdt0 = _torch_np_dtype(keys)
+        vb0 = values.element_size() if values is not None else 0
+        if not NativeComm.supported(kdt0.itemsize, vb0):
+            raise ValueError("protocol='native' takes 4- and 8-byte keys with 0-, 4- or 8-byte values")
+        if receive_items is None:
+            # convenient default: agree on the largest shard (one small all-reduce + host wait per call); pass
+            # receive_items to keep the call free of host waits
+            nmax = torch.tensor([keys.numel()], dtype=torch.int64, device=keys.device)
+            if _staged(dist, group, nmax):
+                nmax = nmax.cpu()
+            dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=group)
+            receive_items = int(nmax.item())
+        cap_items = int(receive_items)
+        comm = NativeComm.get(cap_items * max(kdt0.itemsize, vb0), keys.device, group, dist)
+        ph0 = _Phases(stats is not None and keys.is_cuda, torch)
+        ph0.mark("start")
+        res = comm.sort(keys, values, descending, out=out)
+        ph0.mark("native_sort")
+        if stats is not None:
+            stats["protocol"], stats["exchange"] = "native", "fused"
+            stats["kernel_launches_total"] = comm.kernel_launches
+            stats["phase_ms"] = ph0.result()
+            stats["status"] = comm.status()
+        return res
+    ops = ops or _default_ops()
     rank = dist.get_rank(group)
     kdt = _torch_np_dtype(keys)
     kind, key_bytes = key_kind_of(kdt), kdt.itemsize

@@ -267,6 +267,54 @@ B200RS_API int b200rs_partition_to_peers(
   const uint64_t* h_rank_dst_vals,
   b200rs_stream_t stream);
 
+/*
+ * One-box multi-GPU stable sort (one process per GPU), SURVEY.md 8e / 8(b)-2.
+ *
+ * Replaces cudax::sort over a communicator
+ * (/root/reference/cudax/include/cuda/experimental/__multi_gpu/algorithm/sort/sort.h:96-127; protocol hss/execute.h:56-129),
+ * with the C-ABI shape of /root/reference/c/parallel/include/cccl/c/radix_sort.h:110-124.  Semantics: the concatenation
+ * of the per-rank outputs in rank order equals ONE stable cub::DeviceRadixSort::SortPairs[Descending] of the
+ * concatenation of the per-rank inputs in rank order; rank r's output has as many items as its input; inputs are not
+ * modified.  (The reference's multi-GPU sort is keys-only and unstable; this one is stable and takes values.)
+ *
+ * b200rs_multi_comm_create is COLLECTIVE: every rank calls it with the same `world` and `receive_bytes` (>= the largest
+ * shard's num_items * max(key_bytes, value_bytes) of any later sort) and an all-gather over its own transport
+ * (MPI, torch.distributed, sockets ...): allgather(ctx, send, recv, n) must place the n bytes `send` of rank r at
+ * recv + r * n on every rank and return 0.  It is only used here (CUDA IPC handles); a sort itself makes no host-side
+ * communication, no NCCL call and no host wait: it enqueues a fixed sequence of kernels on `stream`, the small
+ * all-reduces of the splitter selection being done by those kernels over peer-mapped memory (NVLink) and the key/value
+ * exchange being fused into the partition kernel.
+ *
+ * b200rs_sort_multi is COLLECTIVE over the communicator (same key/value widths and order on every rank, any
+ * num_items per rank, zero included); calls on one communicator must be stream-ordered on each rank.  Two-phase
+ * temp-storage query like b200rs_sort.  4- and 8-byte keys with 0-, 4- or 8-byte values, < 2^30 items per rank, up to 16
+ * ranks; other shapes return cudaErrorNotSupported (801).  world == 1 is a plain b200rs_sort.
+ * b200rs_multi_status waits for the device and returns (and clears) the sticky device-side status: 0 ok, 1 a peer
+ * never signalled (timeout), 2 some rank's shard exceeds receive_bytes, 4 internal inconsistency.
+ */
+typedef struct b200rs_multi_comm b200rs_multi_comm;
+typedef int (*b200rs_allgather_fn)(void* ctx, const void* send, void* recv, size_t bytes_per_rank);
+
+B200RS_API int b200rs_multi_comm_create(
+  b200rs_multi_comm** comm, int rank, int world, size_t receive_bytes, b200rs_allgather_fn allgather, void* allgather_ctx);
+B200RS_API int b200rs_multi_comm_destroy(b200rs_multi_comm* comm);
+B200RS_API int b200rs_multi_status(b200rs_multi_comm* comm, int* status);
+B200RS_API int b200rs_multi_last_launch_count(b200rs_multi_comm* comm);
+B200RS_API int b200rs_sort_multi(
+  b200rs_multi_comm* comm,
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int descending,
+  b200rs_stream_t stream);
+
 /* Number of kernel launches / async ops the last b200rs_sort call on this host thread enqueued
  * (bench.py's `gpu_launches`).  Thread-local. */
 B200RS_API int b200rs_last_launch_count(void);

@@ -57,6 +57,8 @@ def _worker(rank, world, port, backend, results, protocol="partition", exchange=
 
     failures = []
     for name, dtype, sizes, dist_name, desc, with_vals in CASES:
+        if protocol == "native" and np.dtype(dtype).itemsize < 4:
+            continue  # b200rs_sort_multi: 4- and 8-byte keys (the Python protocols cover the narrow ones)
         ns = sizes[:world]
         shards, vshards, base = [], [], 0
         for r, n in enumerate(ns):
@@ -72,6 +74,8 @@ def _worker(rank, world, port, backend, results, protocol="partition", exchange=
         stats = {}
         ok, ov = distributed_sort(d_k, d_v, descending=desc, stats=stats, protocol=protocol, exchange=exchange)
         torch.cuda.synchronize()
+        if protocol == "native" and stats.get("status") != 0:
+            failures.append((name, f"device-side status {stats.get('status')}"))
         if backend == "nccl" and sum(ns) > 0 and protocol == "partition":
             want = {"auto": ("fused" if np.dtype(dtype).itemsize >= 4 else "peer"), "peer": "peer",
                     "collective": "collective"}[exchange]
@@ -113,6 +117,12 @@ def _run(world, backend, protocol="partition", exchange="auto"):
 @pytest.mark.parametrize("world", [2, 3])
 def test_distributed_sort_cuda_ranks_sharing_one_gpu(world, protocol):
     _run(world, "gloo", protocol)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_distributed_sort_native_cxx_host():
+    """b200rs_sort_multi (C++ host, kernels only: device-side all-reduce over peer memory, fused exchange)."""
+    _run(min(torch.cuda.device_count(), 3), "nccl", "native")
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
