@@ -564,6 +564,9 @@ def main():
     ap.add_argument("--no-cub", action="store_true", help="skip the cub-on-the-same-GPU context run")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads legs of the default line")
     ap.add_argument("--log2-per-gpu", type=int, default=28, help="multi-GPU: log2 of pairs per GPU")
+    ap.add_argument("--multi-protocol", default="native", choices=["native", "partition", "sort"],
+                    help="multi-GPU: native = b200rs_sort_multi (C++ host, kernels only); partition / sort = the Python "
+                         "host over torch.distributed")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

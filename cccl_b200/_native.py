@@ -27,6 +27,8 @@ EXPORTS = (
     "b200rs_multi_comm_destroy",
     "b200rs_multi_status",
     "b200rs_multi_last_launch_count",
+    "b200rs_multi_timing_enable",
+    "b200rs_multi_timing_read",
     "b200rs_sort_multi",
     "b200rs_last_launch_count",
     "b200rs_set_config",
@@ -91,6 +93,10 @@ def lib() -> ctypes.CDLL:
         l.b200rs_multi_status.argtypes = [vp, ctypes.POINTER(i32)]
         l.b200rs_multi_last_launch_count.restype = i32
         l.b200rs_multi_last_launch_count.argtypes = [vp]
+        l.b200rs_multi_timing_enable.restype = i32
+        l.b200rs_multi_timing_enable.argtypes = [vp, i32]
+        l.b200rs_multi_timing_read.restype = i32
+        l.b200rs_multi_timing_read.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         l.b200rs_sort_multi.restype = i32
         l.b200rs_sort_multi.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, vp, vp, u64, i32, i32, i32, i32, vp]
         l.b200rs_last_launch_count.restype = i32

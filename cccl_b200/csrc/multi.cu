@@ -462,7 +462,23 @@ struct b200rs_multi_comm
   ull seq              = 0;
   size_t off_keys = 0, off_vals = 0;
   int last_launches = 0;
+  bool timing       = false; // record an event at every phase boundary of the next sorts
+  cudaEvent_t ev[5] = {};
+  int ev_used       = 0;
 };
+
+static void mark_phase(b200rs_multi_comm* c, int i, cudaStream_t stream)
+{
+  if (c->timing)
+  {
+    if (c->ev[i] == nullptr)
+    {
+      cudaEventCreate(&c->ev[i]);
+    }
+    cudaEventRecord(c->ev[i], stream);
+    c->ev_used = i + 1;
+  }
+}
 
 static size_t round_up(size_t x, size_t a)
 {
@@ -597,6 +613,13 @@ int b200rs_multi_comm_destroy(b200rs_multi_comm* c)
   cudaFree(c->state);
   cudaFree(c->plan);
   cudaFree(c->hist);
+  for (cudaEvent_t ev : c->ev)
+  {
+    if (ev != nullptr)
+    {
+      cudaEventDestroy(ev);
+    }
+  }
   cudaGetLastError();
   delete c;
   return 0;
@@ -621,6 +644,31 @@ int b200rs_multi_status(b200rs_multi_comm* c, int* status)
 int b200rs_multi_last_launch_count(b200rs_multi_comm* c)
 {
   return c != nullptr ? c->last_launches : 0;
+}
+
+int b200rs_multi_timing_enable(b200rs_multi_comm* c, int on)
+{
+  if (c == nullptr)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  c->timing  = on != 0;
+  c->ev_used = 0;
+  return 0;
+}
+
+int b200rs_multi_timing_read(b200rs_multi_comm* c, float* ms4)
+{
+  if (c == nullptr || ms4 == nullptr || c->ev_used < 5)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  cudaError_t e = cudaEventSynchronize(c->ev[4]);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+  {
+    e = cudaEventElapsedTime(&ms4[i], c->ev[i], c->ev[i + 1]);
+  }
+  return int(e);
 }
 
 int b200rs_sort_multi(
@@ -712,6 +760,7 @@ int b200rs_sort_multi(
   int launches     = 0;
   cudaError_t e    = cudaSuccess;
 
+  mark_phase(c, 0, stream);
   for (int rnd = 0; rnd < key_bytes; ++rnd)
   {
     if (rnd == 0)
@@ -759,6 +808,7 @@ int b200rs_sort_multi(
     }
     ++launches;
   }
+  mark_phase(c, 1, stream);
   // fused partition + exchange: stores go straight into the peers' receive buffers (the previous sort's readers of
   // those buffers are done: every rank's round-0 release above is stream-ordered after its previous final sort)
   if (num_items > 0 && fits)
@@ -771,6 +821,7 @@ int b200rs_sort_multi(
     }
     ++launches;
   }
+  mark_phase(c, 2, stream);
   a.seq = ++c->seq;
   multi_barrier_kernel<<<1, 32, 0, stream>>>(a);
   if ((e = cudaPeekAtLastError()) != cudaSuccess)
@@ -778,6 +829,7 @@ int b200rs_sort_multi(
     return int(e);
   }
   ++launches;
+  mark_phase(c, 3, stream);
   // ONE local stable sort of the received items (source-rank order + stable sort == global stable order)
   if (num_items > 0 && fits)
   {
@@ -791,6 +843,7 @@ int b200rs_sort_multi(
     const int n = b200rs_last_launch_count();
     launches += n > 1 ? n - 1 : n;
   }
+  mark_phase(c, 4, stream);
   c->last_launches = launches;
   return fits ? 0 : int(cudaErrorMemoryAllocation);
 }

@@ -599,6 +599,18 @@ class NativeComm:
         self.kernel_launches += self.lib.b200rs_multi_last_launch_count(self.handle)
         return okeys, ovals
 
+    def timing(self, on):
+        _native.check(self.lib.b200rs_multi_timing_enable(self.handle, int(bool(on))), "b200rs_multi_timing_enable")
+
+    def timing_read(self):
+        """Device ms of the last sort's phases (after timing(True)): splitters, partition (+ exchange), barrier,
+        final_sort."""
+        import ctypes
+
+        ms = (ctypes.c_float * 4)()
+        _native.check(self.lib.b200rs_multi_timing_read(self.handle, ms), "b200rs_multi_timing_read")
+        return dict(zip(("splitters", "partition", "barrier", "final_sort"), (float(x) for x in ms)))
+
     def status(self):
         """Waits for the device; 0 = ok (see include/b200rs.h)."""
         import ctypes
@@ -657,10 +669,12 @@ def distributed_sort(keys, values=None, *, descending=False, group=None, ops=Non
         res = comm.sort(keys, values, descending, out=out)
         ph0.mark("native_sort")
         if stats is not None:
+            # (asking for stats waits for the device; a call without stats enqueues kernels and returns)
             stats["protocol"], stats["exchange"] = "native", "fused"
             stats["kernel_launches_total"] = comm.kernel_launches
             stats["phase_ms"] = ph0.result()
             stats["status"] = comm.status()
+            stats["comm"] = comm
         return res
     ops = ops or _default_ops()
     rank = dist.get_rank(group)

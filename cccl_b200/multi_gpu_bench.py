@@ -40,15 +40,23 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
         torch.cuda.synchronize()
 
     out_buf = (torch.empty_like(keys), torch.empty_like(vals))  # results land here every step (no allocation)
+    proto = getattr(args, "multi_protocol", "native")
+    native = proto == "native"
+    _dsort = distributed_sort
+
+    def distributed_sort(k, v, **kw):  # noqa: F811  (the protocol under test; equal shards: receive_items = n)
+        return _dsort(k, v, protocol=proto, receive_items=n if native else None, **kw)
+
     stats = {}
     for _ in range(args.warmup):
         distributed_sort(keys, vals, stats=stats, out=out_buf)
     barrier()
     from .multi_gpu import _default_ops
 
-    before = _default_ops().kernel_launches
+    counter = stats["comm"] if native else _default_ops()
+    before = counter.kernel_launches
     distributed_sort(keys, vals, out=out_buf)
-    launches = _default_ops().kernel_launches - before  # kernels of libb200rs.so per step on this GPU
+    launches = counter.kernel_launches - before  # kernels of libb200rs.so per step on this GPU
     barrier()
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -57,6 +65,10 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
         barrier()
         ev0.record()
         for _ in range(args.steps):
+            if native:
+                # no stats in the timed loop: the call enqueues kernels and returns (asking for stats would wait)
+                ok, ov = distributed_sort(keys, vals, out=out_buf)
+                continue
             st = {}
             ok, ov = distributed_sort(keys, vals, stats=st, out=out_buf)
             for k, v in st.get("phase_ms", {}).items():
@@ -66,6 +78,21 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
     ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    if native:
+        # phases of a few more (untimed) steps, from events the C++ host records at its phase boundaries
+        comm = stats["comm"]
+        comm.timing(True)
+        for _ in range(5):
+            distributed_sort(keys, vals, out=out_buf)
+            for k, v in comm.timing_read().items():
+                phase.setdefault(k, []).append(v)
+        comm.timing(False)
+        st = {"protocol": "native", "exchange": "fused", "status": comm.status()}
+        assert st["status"] == 0, f"b200rs_sort_multi device-side status {st['status']}"
+        # bytes this rank stores into OTHER GPUs: everything except its own 1/world of a uniform shard (exact count from
+        # the verified result below is not needed for a bandwidth figure)
+        st["exchange_bytes_out"] = int(n * 8 * (world - 1) / world)
+        barrier()
 
     # per-kernel device times of the final local sort of one more (untimed) step
     lib.b200rs_timing_enable(1)
@@ -126,6 +153,32 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
     e2e_ms = torch.tensor([ev0.elapsed_time(ev1) / e2e_steps], device="cuda")
     dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
+
+    # the box's host-copy ceiling: the same H2D and D2H copies of every step, overlapped the same way, on every rank at
+    # the same time, with NO sort in between -- what the PCIe / host-memory side alone allows at this N
+    def copies_only(steps):
+        for i in range(steps):
+            kb, vb = in_bufs[i % 2]
+            ko, vo = out_bufs[i % 2]
+            with torch.cuda.stream(s_in):
+                kb.view(torch.int32).copy_(h_keys, non_blocking=True)
+                vb.view(torch.int32).copy_(h_vals, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_ok.copy_(ko.view(torch.int32), non_blocking=True)
+                h_ov.copy_(vo.view(torch.int32), non_blocking=True)
+        main.wait_stream(s_out)
+        main.wait_stream(s_in)
+
+    copies_only(1)
+    barrier()
+    ev0.record()
+    copies_only(e2e_steps)
+    ev1.record()
+    barrier()
+    copy_ms = torch.tensor([ev0.elapsed_time(ev1) / e2e_steps], device="cuda")
+    dist.all_reduce(copy_ms, op=dist.ReduceOp.MAX)
+    copy_ms = float(copy_ms.item())
+    # restore the shard (in_bufs[0] is keys/vals and holds it already; uploads wrote the same data)
     ok, ov = distributed_sort(keys, vals, out=out_buf)  # keys/vals still hold the shard (uploaded from h_keys/h_vals)
 
     # ---- verification of the last result, on the device, at every N (asserts; the line carries "verified": true).
@@ -182,7 +235,7 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
     barrier()
 
     phase_ms = {k: sum(v) / len(v) for k, v in phase.items()}
-    PH = ("splitters", "partition", "exchange", "final_sort", "local_sort")
+    PH = ("splitters", "partition", "barrier", "exchange", "final_sort", "local_sort")
     ph = torch.tensor([phase_ms.get(k, 0.0) for k in PH], device="cuda")
     dist.all_reduce(ph, op=dist.ReduceOp.MAX)
     xbytes = torch.tensor([float(st.get("exchange_bytes_out", 0))], device="cuda")
@@ -190,9 +243,9 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
     if rank == 0:
         peak, peak_src = measured_peaks()
         fused = st.get("exchange") == "fused"
-        ex_ms = float(ph[1]) if fused else float(ph[2])  # fused: the partition kernel IS the exchange
+        ex_ms = float(ph[1]) if fused else float(ph[3])  # fused: the partition kernel IS the exchange
         one = 2.0 * n * 8  # bytes one onesweep pass moves per GPU
-        sort_ms = float(ph[3])
+        sort_ms = float(ph[4])
         line = {
             "metric": metric,
             "value": total / (ms * 1e-3) / 1e9,
@@ -209,6 +262,9 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
             "config": {"workload": workload_name, "keys": "uint32", "values": "uint32", "pairs_per_gpu": n,
                        "total_pairs": total, "distribution": "uniform", "parallelism": f"range-partition x{world}",
                        "protocol": st.get("protocol"),
+                       "host": ("C++ (b200rs_sort_multi): kernels only, select-round all-reduces over peer-mapped memory, "
+                                "no NCCL call and no host wait per sort") if native else
+                               "Python over torch.distributed (NCCL all-reduces, symmetric memory)",
                        "exchange": {"fused": "fused into the partition kernel: direct stores into the destination GPUs' "
                                              "symmetric-memory receive buffers over NVLink 5 / NVSwitch",
                                     "peer": "direct peer copies into symmetric-memory receive buffers over NVLink 5 / "
@@ -236,7 +292,11 @@ def run(args, metric, workload_name, ClockSampler, measured_peaks):
             "cpu_baseline": None,
             "e2e": {"value": total / (e2e_ms * 1e-3) / 1e9, "unit": "Gkeys/s", "h2d_bytes_per_step": n * 8 * world,
                     "d2h_bytes_per_step": n * 8 * world, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "overlap": "H2D of step i+1 and D2H of step i on copy streams while the sort runs"},
+                    "overlap": "H2D of step i+1 and D2H of step i on copy streams while the sort runs",
+                    "copies_only_ms_per_step": copy_ms,
+                    "host_copy_ceiling_GBps_per_gpu_per_direction": n * 8 / (copy_ms * 1e-3) / 1e9,
+                    "note": "copies_only = the same pinned-host H2D + D2H of every step on all ranks at once with no "
+                            "sort in between: the part of e2e the box's PCIe / host memory sets"},
             "gpu_launches": launches * args.steps * world,
             "gpu_launches_per_step_per_gpu": launches,
             "clocks": clocks.summary(),

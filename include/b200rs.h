@@ -300,6 +300,11 @@ B200RS_API int b200rs_multi_comm_create(
 B200RS_API int b200rs_multi_comm_destroy(b200rs_multi_comm* comm);
 B200RS_API int b200rs_multi_status(b200rs_multi_comm* comm, int* status);
 B200RS_API int b200rs_multi_last_launch_count(b200rs_multi_comm* comm);
+/* Per-phase device time of the next sorts on this communicator (bench.py): while enabled b200rs_sort_multi records an
+ * event on `stream` at every phase boundary; b200rs_multi_timing_read waits for the last sort and writes
+ * ms4 = {splitter selection, fused partition + exchange, cross-GPU barrier, final local sort}. */
+B200RS_API int b200rs_multi_timing_enable(b200rs_multi_comm* comm, int on);
+B200RS_API int b200rs_multi_timing_read(b200rs_multi_comm* comm, float* ms4);
 B200RS_API int b200rs_sort_multi(
   b200rs_multi_comm* comm,
   void* d_temp_storage,

@@ -119,6 +119,14 @@ def test_distributed_sort_cuda_ranks_sharing_one_gpu(world, protocol):
     _run(world, "gloo", protocol)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_sort_native_cxx_host_ranks_sharing_one_gpu(world):
+    """b200rs_sort_multi with the ranks as processes on ONE GPU (CUDA IPC between contexts of the same device; the
+    kernels of one rank wait for flags the other ranks' kernels set, which the driver's time slicing lets happen), so
+    the C++ host, the device-side all-reduce and the fused exchange are exercised on a one-GPU box too."""
+    _run(world, "gloo", "native")
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_distributed_sort_native_cxx_host():
     """b200rs_sort_multi (C++ host, kernels only: device-side all-reduce over peer memory, fused exchange)."""
