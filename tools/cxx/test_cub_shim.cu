@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -384,14 +385,95 @@ void half_keys(size_t n, bool descending)
   REQUIRE(same);
 }
 
+// The multi-GPU partition pass through the C ABI (b200rs_partition_by_splitters): stable partition of (u32 key, u32
+// value) pairs into destination-bucket order, bucket = 2 * #{splitters below} + [equals a splitter]; host check.
+void partition_case(size_t n, int and_rounds)
+{
+  std::mt19937_64 rng(99 + n);
+  std::vector<uint32_t> hk(n), hv(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    uint32_t k = uint32_t(rng());
+    for (int r = 1; r < and_rounds; ++r)
+    {
+      k &= uint32_t(rng());
+    }
+    hk[i] = k;
+    hv[i] = uint32_t(i);
+  }
+  std::vector<uint32_t> sorted(hk);
+  std::sort(sorted.begin(), sorted.end());
+  std::vector<uint64_t> sp;
+  for (int q = 1; q < 4 && n > 0; ++q)
+  {
+    const uint64_t v = sorted[n * q / 4];
+    if (sp.empty() || sp.back() < v)
+    {
+      sp.push_back(v);
+    }
+  }
+  const int ns = int(sp.size()), nb = 2 * ns + 1;
+  auto bucket = [&](uint32_t k) {
+    int id = 0;
+    for (int j = 0; j < ns; ++j)
+    {
+      id += (k > sp[j] ? 1 : 0) + (k >= sp[j] ? 1 : 0);
+    }
+    return id;
+  };
+  std::vector<uint64_t> sizes(nb, 0), offs(nb, 0);
+  for (size_t i = 0; i < n; ++i)
+  {
+    ++sizes[bucket(hk[i])];
+  }
+  for (int b = 1; b < nb; ++b)
+  {
+    offs[b] = offs[b - 1] + sizes[b - 1];
+  }
+  std::vector<uint32_t> ek(n), ev(n);
+  {
+    std::vector<uint64_t> cur(offs);
+    for (size_t i = 0; i < n; ++i)
+    {
+      const uint64_t at = cur[bucket(hk[i])]++;
+      ek[at]            = hk[i];
+      ev[at]            = hv[i];
+    }
+  }
+  dev<uint32_t> dk(hk), dv(hv), ok(n), ov(n);
+  size_t bytes = 0;
+  int rc = b200rs_partition_by_splitters(nullptr, &bytes, nullptr, nullptr, nullptr, nullptr, n, B200RS_KEY_UINT, 4, 4, 0,
+                                         sp.data(), ns, offs.data(), nullptr);
+  REQUIRE(rc == 0);
+  dev<unsigned char> temp(bytes);
+  rc = b200rs_partition_by_splitters(temp.p, &bytes, dk.p, ok.p, dv.p, ov.p, n, B200RS_KEY_UINT, 4, 4, 0, sp.data(), ns,
+                                     offs.data(), nullptr);
+  REQUIRE(rc == 0);
+  REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+  REQUIRE(ok.host() == ek);
+  REQUIRE(ov.host() == ev);
+}
+
 int main()
 {
   cudaStream_t stream;
   cudaStreamCreate(&stream);
+  // compute-sanitizer runs (tools/sanitize.sh) cap the problem size: racecheck is ~100x slower than native
+  const char* cap_env  = getenv("B200RS_TEST_MAX_N");
+  const size_t max_n   = cap_env != nullptr ? size_t(atoll(cap_env)) : ~size_t(0);
   env_api_goldens();
   edge_cases();
+  for (size_t n : {size_t(3000), size_t(77777)})
+  {
+    partition_case(n, 1);
+    partition_case(n, 4);
+  }
   for (size_t n : {size_t(1000), size_t(300007)})
   {
+    if (n > max_n)
+    {
+      continue;
+    }
     half_keys<__half>(n, false);
     half_keys<__half>(n, true);
     half_keys<__nv_bfloat16>(n, false);
@@ -400,6 +482,10 @@ int main()
   const size_t sizes[] = {1, 2, 255, 4864, 4865, 100000, (1u << 21) + 17};
   for (size_t n : sizes)
   {
+    if (n > max_n)
+    {
+      continue;
+    }
     check_keys<uint32_t>(n, false, 0, 32, false, stream);
     check_keys<int32_t>(n, true, 0, 32, true, stream);
     check_keys<float>(n, true, 8, 24, false, nullptr);
