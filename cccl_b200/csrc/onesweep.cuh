@@ -302,6 +302,59 @@ __device__ __forceinline__ unsigned long long peer_address(
   return p + (unsigned long long) idx * item_bytes;
 }
 
+// Bucket mode with remote destinations, the scatter: run by run (one run = the tile's items of one bucket, contiguous
+// at the destination), every warp store covering ONE 128-byte-aligned line of the destination.  Measured on B200
+// (tools/ubench/peer_store.cu): SM stores into a peer GPU reach 700 GB/s when each warp's 128 bytes are line-aligned,
+// 410-420 GB/s when they straddle two lines -- which is what a position-order scatter does, runs starting anywhere.
+// s_end[b] = end of bucket b's staged run, s_goff[b] + staged position = partitioned index.
+template <class T, int NT, class F>
+__device__ __forceinline__ void scatter_runs_to_peers(
+  uint32_t s_end, uint32_t s_goff, uint32_t s_peer, uint32_t bucket_table_off, uint32_t rank_table_off, uint32_t s_data,
+  uint32_t num_buckets, uint32_t valid, F on_store)
+{
+  constexpr uint32_t NW   = NT / 32;
+  constexpr uint32_t LINE = 128 / sizeof(T) < 32 ? 32 : 128 / sizeof(T); // items per warp store (>= one line)
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t start = 0;
+  for (uint32_t b = 0; b < num_buckets; ++b)
+  {
+    const uint32_t end  = lds32(s_end + b * 4);
+    const uint32_t stop = end < valid ? end : valid;
+    if (stop > start)
+    {
+      const uint32_t goff          = lds32(s_goff + b * 4);
+      const unsigned long long ptr = lds64(s_peer + bucket_table_off + b * 8);
+      if (ptr != 0)
+      {
+        // byte address of the run's first item; m = items between the previous line boundary and it
+        const unsigned long long first = ptr + (unsigned long long) (goff + start) * sizeof(T);
+        const uint32_t m               = uint32_t(first & 127u) / uint32_t(sizeof(T));
+        const uint32_t count           = stop - start;
+        const uint32_t lines           = (count + m + LINE - 1) / LINE;
+        for (uint32_t l = warp; l < lines; l += NW)
+        {
+          const uint32_t v = l * LINE + lane;
+          if (v >= m && v - m < count)
+          {
+            const T x = lds_t<T>(s_data + (start + v - m) * uint32_t(sizeof(T)));
+            *reinterpret_cast<T*>(first + (unsigned long long) (v - m) * sizeof(T)) = on_store(x);
+          }
+        }
+      }
+      else // a segment boundary falls inside this bucket (keys tied with a splitter): destination per item
+      {
+        for (uint32_t p = start + threadIdx.x; p < stop; p += NT)
+        {
+          const T x = lds_t<T>(s_data + p * uint32_t(sizeof(T)));
+          *reinterpret_cast<T*>(peer_address(s_peer, bucket_table_off, rank_table_off, b, goff + p, uint32_t(sizeof(T)))) =
+            on_store(x);
+        }
+      }
+    }
+    start = end;
+  }
+}
+
 // warp counters: 32-bit, or 16-bit (OPT_CTR16: two digits per word, so a warp-wide access touches at most four
 // distinct words per bank instead of eight)
 template <bool C16>
@@ -865,6 +918,39 @@ __device__ __forceinline__ void onesweep_tile(
       }
     }
     return;
+  }
+
+  if constexpr (BUCKET)
+  {
+    if (a.peer != nullptr)
+    {
+      // remote destinations: line-aligned run-by-run scatter (keys, then values through the same staging buffer)
+      const XformT<U> xf(a.xf);
+      const uint32_t nbuckets = 2u * lds32(sbase + L::OFF_SPLIT + 128) + 1u;
+      const bool last         = a.last_pass != 0;
+      scatter_runs_to_peers<U, NT>(sbase + L::OFF_END, s_goff, sbase + L::OFF_PEER,
+                                   uint32_t(offsetof(PeerTable, bucket_dst_keys)),
+                                   uint32_t(offsetof(PeerTable, rank_dst_keys)), s_data, nbuckets, valid,
+                                   [&](U k) { return last ? twiddle_out(k, xf) : k; });
+      if constexpr (VBYTES > 0)
+      {
+        __syncthreads(); // staged keys are dead
+#pragma unroll
+        for (int i = 0; i < IPT; ++i)
+        {
+          if (FULL || chunk + i * 32 < valid)
+          {
+            sts_t<V>(s_data - uint32_t(sizeof(V)) + (get16(rank2, i) >> CSH) * uint32_t(sizeof(V)), val[i]);
+          }
+        }
+        __syncthreads();
+        scatter_runs_to_peers<V, NT>(sbase + L::OFF_END, s_goff, sbase + L::OFF_PEER,
+                                     uint32_t(offsetof(PeerTable, bucket_dst_vals)),
+                                     uint32_t(offsetof(PeerTable, rank_dst_vals)), s_data, nbuckets, valid,
+                                     [](V v) { return v; });
+      }
+      return;
+    }
   }
 
   // ---- coalesced scatter: consecutive threads write consecutive staged positions
