@@ -79,7 +79,12 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
     s_first[threadIdx.x]  = first;
     if (one_byte_prefix && first == int(threadIdx.x))
     {
-      s_row[pf & (RADIX - 1)] = (signed char) threadIdx.x;
+      // integer keys: the table is indexed by the RAW top byte (sign / descending flips folded into the index), so the
+      // scan below tests a key with one shift and one byte load; float keys go through the transform (the -0.0 rule
+      // and the sign-dependent flip need the whole key)
+      const unsigned int flips = (unsigned int) ((kx.sign_mask ^ kx.desc_mask) >> (sizeof(U) * 8 - RADIX_BITS));
+      const unsigned int idx   = kx.float_mask != 0 ? (unsigned int) pf : ((unsigned int) pf ^ flips);
+      s_row[idx & (RADIX - 1)] = (signed char) threadIdx.x;
     }
   }
   __syncthreads();
@@ -102,14 +107,15 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
   const unsigned long long stride   = from_slice ? per_iter : (unsigned long long) gridDim.x * per_iter;
   const unsigned long long start    = from_slice ? 0ull : (unsigned long long) blockIdx.x * per_iter;
   // whole blocks iterate together (the trip count only depends on blockIdx) so the votes below are convergent
-  for (unsigned long long base = start; base < n; base += stride)
-  {
+  const bool is_float = kx.float_mask != 0;
+  auto body           = [&](auto check_tag, unsigned long long base) {
+    constexpr bool CHECK = decltype(check_tag)::value; // only the last iteration of a block can run past n
     Vec raw[LOADS];
 #pragma unroll
     for (int l = 0; l < LOADS; ++l)
     {
       const unsigned long long i = base + ((unsigned long long) l * PART_THREADS + threadIdx.x) * VEC;
-      if (i + VEC <= n)
+      if (!CHECK || i + VEC <= n)
       {
         raw[l] = *reinterpret_cast<const Vec*>(keys + i);
       }
@@ -129,28 +135,36 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
       for (int j = 0; j < VEC; ++j)
       {
         const unsigned long long i = base + ((unsigned long long) l * PART_THREADS + threadIdx.x) * VEC + j;
-        const U v                  = digit_view(twiddle_in(raw[l].k[j], xf), xf);
-        // hi_shift == key bits on the first round: every key carries the (empty) prefix
-        const unsigned long long hi = hi_shift >= int(sizeof(U) * 8) ? 0ull : (unsigned long long) (v >> hi_shift);
-        const unsigned int bin      = (unsigned int) (v >> lo_shift) & (RADIX - 1);
-        int row = -1;
+        const bool inside          = !CHECK || i < n;
+        int row                    = -1;
+        U v                        = raw[l].k[j];
         if (one_byte_prefix)
         {
-          // one table look-up instead of a loop over the prefixes: this is the only round that scans every key
-          row = i < n ? int(s_row[hi & (RADIX - 1)]) : -1;
+          // the only round that scans every key: one table look-up per key (integer keys: on the raw top byte)
+          if (is_float)
+          {
+            v = digit_view(twiddle_in(v, xf), xf);
+          }
+          row = inside ? int(s_row[(unsigned int) (v >> (sizeof(U) * 8 - RADIX_BITS)) & (RADIX - 1)]) : -1;
           if (!__any_sync(0xffffffffu, row >= 0))
           {
             continue;
           }
+          if (!is_float)
+          {
+            v = digit_view(twiddle_in(v, xf), xf);
+          }
         }
         else
         {
-          const bool maybe = i < n;
-          if (!__any_sync(0xffffffffu, maybe))
+          if (!__any_sync(0xffffffffu, inside))
           {
             continue;
           }
-          if (maybe)
+          v = digit_view(twiddle_in(v, xf), xf);
+          // hi_shift == key bits on the first round: every key carries the (empty) prefix
+          const unsigned long long hi = hi_shift >= int(sizeof(U) * 8) ? 0ull : (unsigned long long) (v >> hi_shift);
+          if (inside)
           {
             for (int p = 0; p < np; ++p)
             {
@@ -158,8 +172,9 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
             }
           }
         }
-        const bool hit        = row >= 0;
-        const unsigned int hm = __ballot_sync(0xffffffffu, hit);
+        const unsigned int bin = (unsigned int) (v >> lo_shift) & (RADIX - 1);
+        const bool hit         = row >= 0;
+        const unsigned int hm  = __ballot_sync(0xffffffffu, hit);
         if (hit)
         {
           const unsigned int slot = (unsigned int) row * RADIX + bin;
@@ -200,6 +215,17 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
           }
         }
       }
+    }
+  };
+  for (unsigned long long base = start; base < n; base += stride)
+  {
+    if (base + per_iter <= n)
+    {
+      body(std::false_type{}, base);
+    }
+    else
+    {
+      body(std::true_type{}, base);
     }
   }
   __syncthreads();
