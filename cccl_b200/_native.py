@@ -35,6 +35,7 @@ EXPORTS = (
     "b200rs_set_portion_items",
     "b200rs_set_force_big",
     "b200rs_set_single_tile",
+    "b200rs_set_small_max",
     "b200rs_describe_config",
     "b200rs_timing_enable",
     "b200rs_timing_read",
@@ -107,6 +108,8 @@ def lib() -> ctypes.CDLL:
         l.b200rs_set_portion_items.argtypes = [ctypes.c_ulonglong]
         l.b200rs_set_force_big.restype = i32
         l.b200rs_set_force_big.argtypes = [i32]
+        l.b200rs_set_small_max.restype = i32
+        l.b200rs_set_small_max.argtypes = [ctypes.c_ulonglong]
         l.b200rs_set_single_tile.restype = i32
         l.b200rs_set_single_tile.argtypes = [i32]
         l.b200rs_describe_config.restype = i32
@@ -137,7 +140,7 @@ def sort_raw(d_temp: int, temp_bytes: int, keys_in: int, keys_out: int, vals_in:
     return nbytes.value, selector.value
 
 
-OP_NAMES = ("memset", "histogram", "scan", "onesweep", "copy", "single_tile")
+OP_NAMES = ("memset", "histogram", "scan", "onesweep", "copy", "single_tile", "small_sort")
 
 
 def timing_read():

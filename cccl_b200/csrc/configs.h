@@ -44,6 +44,12 @@ cudaError_t launch_single_tile(
   const void* keys_in, void* keys_out, const void* vals_in, void* vals_out, unsigned long long n, int key_bytes,
   int value_bytes, int begin_bit, int end_bit, const KeyXform& xf, cudaStream_t stream);
 
+// the whole sort of a mid-size input in one cooperative launch (small.cu); `passes` is what the general path would launch
+bool small_sort_supported(int key_bytes, int value_bytes);
+unsigned long long small_sort_tile_items();
+cudaError_t launch_small_sort(const PassArgs* passes, int num_passes, unsigned long long* bins, unsigned tiles,
+                              int key_bytes, int value_bytes, int sms, cudaStream_t stream);
+
 cudaError_t launch_splitter_ranks(
   const void* sorted_keys, unsigned long long n, int key_bytes, const KeyXform& xf, const void* splitters,
   int num_splitters, unsigned long long* lt, unsigned long long* eq, cudaStream_t stream);

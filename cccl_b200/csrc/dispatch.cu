@@ -23,6 +23,9 @@ static std::atomic<int> g_config_override{-1};
 static std::atomic<unsigned long long> g_portion_override{0};
 static std::atomic<bool> g_force_big{false};
 static std::atomic<bool> g_no_single_tile{false};
+// inputs of at most this many items take the one-launch cooperative kernel (small.cu); tuned on B200 with
+// tools/size_sweep.py (the general path wins from about 2^21 items on)
+static std::atomic<unsigned long long> g_small_max{1ull << 20};
 static thread_local int t_last_launches = 0;
 
 // Optional per-op device timing (bench.py's roofline leg): when enabled, an event is recorded on the stream before
@@ -41,7 +44,8 @@ enum OpKind
   OP_SCAN      = 2,
   OP_ONESWEEP  = 3,
   OP_COPY      = 4,
-  OP_SINGLE    = 5
+  OP_SINGLE    = 5,
+  OP_SMALL     = 6
 };
 
 static void mark_op(cudaStream_t stream, int kind)
@@ -227,7 +231,13 @@ B200RS_API int b200rs_set_force_big(int on)
 }
 
 // diagnostic: route inputs of at most one tile through the general path as well (tests compare both)
-B200RS_API int b200rs_set_single_tile(int on)
+B200RS_API int b200rs_set_small_max(unsigned long long items)
+{
+  g_small_max.store(items, std::memory_order_relaxed);
+  return 0;
+}
+
+int b200rs_set_single_tile(int on)
 {
   g_no_single_tile.store(on == 0, std::memory_order_relaxed);
   return 0;
@@ -449,6 +459,19 @@ int b200rs_sort(
   PortionPlan plan       = plan_portions(num_items, uint64_t(cfg->tile_items));
   uint64_t size_portions = plan.portions;
   uint64_t size_tiles    = plan.max_tiles;
+  // mid-size inputs: every phase of the sort in ONE cooperative launch (small.cu).  Not with a forced configuration,
+  // forced 64-bit offsets or a portion override: those diagnostics are about the general path.
+  const bool small = small_sort_supported(key_bytes, value_bytes) && passes <= 8
+                  && num_items <= g_small_max.load(std::memory_order_relaxed) && plan.portions == 1
+                  && g_config_override.load(std::memory_order_relaxed) < 0 && !g_force_big.load(std::memory_order_relaxed)
+                  && g_portion_override.load(std::memory_order_relaxed) == 0;
+  if (small)
+  {
+    fb            = nullptr;
+    plan          = plan_portions(num_items, small_sort_tile_items());
+    size_portions = plan.portions;
+    size_tiles    = plan.max_tiles;
+  }
   if (fb != nullptr)
   {
     const PortionPlan alt = plan_portions(num_items, uint64_t(fb->tile_items));
@@ -517,24 +540,29 @@ int b200rs_sort(
   const KeyXform xf =
     make_xform(key_kind, key_bytes, descending, num_items <= reference_single_tile_items(key_bytes, value_bytes));
 
-  mark_op(stream, OP_MEMSET);
-  cudaError_t e = cudaMemsetAsync(base, 0, L.control_bytes, stream);
-  if (e != cudaSuccess)
+  cudaError_t e = cudaSuccess;
+  PassArgs small_pass[8];
+  if (!small)
   {
-    return int(e);
-  }
-  // upsweep over the whole input: counts land in portion 0's bins, then become exclusive offsets
-  mark_op(stream, OP_HISTOGRAM);
-  e = launch_histogram(d_keys_in, num_items, key_bytes, bins, passes, begin_bit, end_bit, xf, sms, stream);
-  if (e != cudaSuccess)
-  {
-    return int(e);
-  }
-  mark_op(stream, OP_SCAN);
-  e = launch_scan_bins(bins, passes, stream);
-  if (e != cudaSuccess)
-  {
-    return int(e);
+    mark_op(stream, OP_MEMSET);
+    e = cudaMemsetAsync(base, 0, L.control_bytes, stream);
+    if (e != cudaSuccess)
+    {
+      return int(e);
+    }
+    // upsweep over the whole input: counts land in portion 0's bins, then become exclusive offsets
+    mark_op(stream, OP_HISTOGRAM);
+    e = launch_histogram(d_keys_in, num_items, key_bytes, bins, passes, begin_bit, end_bit, xf, sms, stream);
+    if (e != cudaSuccess)
+    {
+      return int(e);
+    }
+    mark_op(stream, OP_SCAN);
+    e = launch_scan_bins(bins, passes, stream);
+    if (e != cudaSuccess)
+    {
+      return int(e);
+    }
   }
 
   const uint64_t launches = uint64_t(passes) * portions;
@@ -600,6 +628,11 @@ int b200rs_sort(
       a.peer          = nullptr;
       a.plan          = nullptr;
       a.sm_count      = sms;
+      if (small)
+      {
+        small_pass[pass] = a; // (one portion) launched together below
+        continue;
+      }
       mark_op(stream, OP_ONESWEEP);
       e = cfg->launch(a, tiles, stream);
       if (e != cudaSuccess)
@@ -609,6 +642,15 @@ int b200rs_sort(
     }
     src_k = dst_k;
     src_v = dst_v;
+  }
+  if (small)
+  {
+    mark_op(stream, OP_SMALL);
+    e = launch_small_sort(small_pass, passes, bins, unsigned(plan.max_tiles), key_bytes, value_bytes, sms, stream);
+    if (e != cudaSuccess)
+    {
+      return int(e);
+    }
   }
   mark_end(stream);
   if (selector != nullptr)

@@ -58,7 +58,11 @@ enum OnesweepOpt
   // 4-byte keys, 16-bit counters: the digit is extracted already scaled and merged with the table base (one rotate +
   // one LOP3 give the shared-memory address), and the scatter folds the staged position into a per-thread pointer
   OPT_FOLD        = 256,
-  OPT_FOLD_PTR    = 512 // with OPT_FOLD: scatter through a per-thread pointer + biased offsets instead of offset + position
+  OPT_FOLD_PTR    = 512, // with OPT_FOLD: scatter through a per-thread pointer + biased offsets instead of offset + position
+  // __syncwarp() between the group leader's counter store and the next row's counter loads.  The hardware executes a
+  // converged warp's shared-memory instructions in order, so results do not depend on it, but the CUDA memory model does
+  // not promise that and compute-sanitizer racecheck reports the pair as a hazard (profiles/r2t_sanitizer.txt)
+  OPT_SYNCWARP    = 1024
 };
 
 template <class U, int VBYTES, int NT, int IPT, int OPT = 0>
@@ -708,6 +712,10 @@ __device__ __forceinline__ void onesweep_tile(
     if ((b & c & gt_mask) == 0) // highest peer lane: its position + 1 is the new running count
     {
       ctr_st<C16>(ctr, next);
+    }
+    if (OPT & OPT_SYNCWARP)
+    {
+      __syncwarp();
     }
     put16(rank2, i, next);
   }

@@ -186,6 +186,7 @@ __device__ __forceinline__ void onesweep_tma_tile(
     {
       sts32(ctr, next);
     }
+    __syncwarp(); // the next row's loads of this counter come after the leader's store (memory model, racecheck)
     put16(rank2, i, next);
   }
   __syncthreads();

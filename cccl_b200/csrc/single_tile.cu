@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(ST_THREADS) single_tile_kernel(const SingleTil
       {
         ctr_st<true>(ctr, next);
       }
+      __syncwarp(); // the next row's loads of this counter come after the leader's store (memory model, racecheck)
       rank[i] = next - 1;
     }
     __syncthreads();

@@ -348,6 +348,12 @@ B200RS_API int b200rs_set_force_big(int on);
  * tests can compare the two; 1 (default) restores the single-CTA kernel. */
 B200RS_API int b200rs_set_single_tile(int on);
 
+/* Tuning/diagnostic: inputs of at most `items` items (4- or 8-byte keys with 0-, 4- or 8-byte values) are sorted by ONE
+ * cooperative launch that runs every phase of the general path between grid-wide barriers (the latency path; the
+ * reference uses programmatic dependent launch for the same regime, dispatch_radix_sort.cuh:1755-1756).  Default 2^20;
+ * 0 sends everything above one tile through the general multi-kernel path. */
+B200RS_API int b200rs_set_small_max(unsigned long long items);
+
 /* Human-readable description of configuration `config_index` for (key_bytes, value_bytes); returns the number of
  * configurations available when config_index < 0.  buf may be NULL. */
 B200RS_API int b200rs_describe_config(int key_bytes, int value_bytes, int config_index, char* buf, size_t buf_len);

@@ -18,6 +18,18 @@ KEY_DTYPES = [np.uint8, np.int8, np.uint16, np.int16, np.float16, np.uint32, np.
               np.float64]
 
 
+@pytest.fixture(params=["fused_small", "general"])
+def sort_path(request):
+    """Inputs up to 2^20 items (4- / 8-byte keys with 0- / 4- / 8-byte values) take the one-launch cooperative kernel
+    (csrc/small.cu) by default; "general" switches it off so that the same cases also exercise the multi-kernel path."""
+    from cccl_b200 import _native
+
+    lib = _native.lib()
+    lib.b200rs_set_small_max(0 if request.param == "general" else (1 << 20))
+    yield request.param
+    lib.b200rs_set_small_max(1 << 20)
+
+
 def check_keys(k, **kw):
     got, info = gpu_sort(k, **kw)
     okw = {x: kw[x] for x in ("descending", "begin_bit", "end_bit") if x in kw}
@@ -66,7 +78,7 @@ def test_committed_golden_fixtures_on_gpu():
 
 @pytest.mark.parametrize("dtype", KEY_DTYPES)
 @pytest.mark.parametrize("descending", [False, True])
-def test_keys_all_types_sizes(dtype, descending):
+def test_keys_all_types_sizes(dtype, descending, sort_path):
     rng = np.random.default_rng(11)
     sizes = [0, 1, 2, 31, 32, 33, 255, 4095, 4096, 4097, 8191, 8192, 8193, 12289, 100_003]
     sizes += rng.integers(32, 1 << 20, size=3).tolist()
@@ -75,7 +87,7 @@ def test_keys_all_types_sizes(dtype, descending):
 
 
 @pytest.mark.parametrize("dtype", [np.uint32, np.uint64, np.float32, np.int64, np.uint16, np.uint8])
-def test_bit_windows(dtype):
+def test_bit_windows(dtype, sort_path):
     bits = np.dtype(dtype).itemsize * 8
     cuts = sorted({0, bits // 3, 3 * bits // 4, bits})
     k = make_keys("uniform", 70_001, dtype, seed=9)
@@ -89,7 +101,7 @@ def test_bit_windows(dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float16, np.float32, np.float64])
-def test_signed_zeros_and_nans(dtype):
+def test_signed_zeros_and_nans(dtype, sort_path):
     udt = {np.float16: np.uint16, np.float32: np.uint32, np.float64: np.uint64}[dtype]
     n = 50_000
     rng = np.random.default_rng(2)
@@ -112,7 +124,7 @@ def test_signed_zeros_and_nans(dtype):
 @pytest.mark.parametrize("dist", ["entropy2", "entropy3", "entropy5", "equal", "few2", "few16", "few256", "sorted",
                                   "reverse"])
 @pytest.mark.parametrize("dtype", [np.uint32, np.uint64])
-def test_skewed_distributions_pairs_stable(dist, dtype):
+def test_skewed_distributions_pairs_stable(dist, dtype, sort_path):
     n = 300_007
     k = make_keys(dist, n, dtype, seed=21)
     v = make_values(n, np.uint32)
@@ -122,7 +134,7 @@ def test_skewed_distributions_pairs_stable(dist, dtype):
 
 @pytest.mark.parametrize("vdtype", [np.uint8, np.uint16, np.uint32, np.uint64, V16])
 @pytest.mark.parametrize("kdtype", [np.uint8, np.uint16, np.uint32, np.uint64])
-def test_value_widths(kdtype, vdtype):
+def test_value_widths(kdtype, vdtype, sort_path):
     for n in (1, 777, 40_000):
         k = make_keys("few256" if n > 1000 else "uniform", n, kdtype, seed=n)
         v = make_values(n, vdtype)
@@ -158,13 +170,20 @@ def test_single_tile_kernel_and_general_path_agree(kdtype):
                     assert info["temp_bytes"] == 1
                     try:
                         lib.b200rs_set_single_tile(0)
+                        # without the single-CTA kernel: the one-launch cooperative kernel where it is compiled ...
                         info2 = check_pairs(k, v, **kw) if v is not None else check_keys(k, **kw)
-                        assert info2["launches"] > 1
+                        fused = np.dtype(kdtype).itemsize in (4, 8) and (vdtype is None or np.dtype(vdtype).itemsize in (4, 8))
+                        assert (info2["launches"] == 1) == fused, (n, info2)
+                        # ... and the general multi-kernel path
+                        lib.b200rs_set_small_max(0)
+                        info3 = check_pairs(k, v, **kw) if v is not None else check_keys(k, **kw)
+                        assert info3["launches"] > 1
                     finally:
                         lib.b200rs_set_single_tile(1)
+                        lib.b200rs_set_small_max(1 << 20)
 
 
-def test_double_buffer_selector_and_pass_parity():
+def test_double_buffer_selector_and_pass_parity(sort_path):
     # result is wherever selector says (catch2_test_device_radix_sort_keys.cu:441-446)
     k = make_keys("uniform", 50_000, np.uint32, seed=8)
     for e, want_sel in ((8, 1), (16, 0), (24, 1), (32, 0)):
@@ -176,7 +195,7 @@ def test_double_buffer_selector_and_pass_parity():
     assert info["selector"] == 1
 
 
-def test_unaligned_temp_storage_and_streams():
+def test_unaligned_temp_storage_and_streams(sort_path):
     k = make_keys("uniform", 123_457, np.uint32, seed=1)
     v = make_values(k.size, np.uint64)
     check_pairs(k, v, temp_misalign=3)
@@ -239,7 +258,7 @@ def test_upsweep_histogram_alone(dtype):
     assert np.array_equal(got, oracle_histogram(k, begin_bit=bits // 3, end_bit=bits - 1))
 
 
-def test_cuda_graph_capture():
+def test_cuda_graph_capture(sort_path):
     """The execute call is allocation-free and stream-ordered: legal under capture
     (cub/test/catch2_test_launch_helper.h:91-121)."""
     from cccl_b200 import _native
