@@ -23,9 +23,11 @@ static std::atomic<int> g_config_override{-1};
 static std::atomic<unsigned long long> g_portion_override{0};
 static std::atomic<bool> g_force_big{false};
 static std::atomic<bool> g_no_single_tile{false};
-// inputs of at most this many items take the one-launch cooperative kernel (small.cu); tuned on B200 with
-// tools/size_sweep.py (the general path wins from about 2^21 items on)
-static std::atomic<unsigned long long> g_small_max{1ull << 20};
+// inputs of at most this many KEY BYTES take the one-launch cooperative kernel (small.cu); measured on B200 with
+// tools/ubench/small_crossover.py: 2.0-2.3x faster than the general path up to 2^16 items, level at 4 MiB of keys
+// (2^20 4-byte keys / 2^19 8-byte keys), behind from there on.  b200rs_set_small_max overrides it in items.
+static std::atomic<unsigned long long> g_small_max{~0ull};
+constexpr unsigned long long SMALL_MAX_KEY_BYTES = 4ull << 20;
 static thread_local int t_last_launches = 0;
 
 // Optional per-op device timing (bench.py's roofline leg): when enabled, an event is recorded on the stream before
@@ -462,7 +464,10 @@ int b200rs_sort(
   // mid-size inputs: every phase of the sort in ONE cooperative launch (small.cu).  Not with a forced configuration,
   // forced 64-bit offsets or a portion override: those diagnostics are about the general path.
   const bool small = small_sort_supported(key_bytes, value_bytes) && passes <= 8
-                  && num_items <= g_small_max.load(std::memory_order_relaxed) && plan.portions == 1
+                  && (g_small_max.load(std::memory_order_relaxed) == ~0ull
+                        ? num_items * uint64_t(key_bytes) <= SMALL_MAX_KEY_BYTES
+                        : num_items <= g_small_max.load(std::memory_order_relaxed))
+                  && plan.portions == 1
                   && g_config_override.load(std::memory_order_relaxed) < 0 && !g_force_big.load(std::memory_order_relaxed)
                   && g_portion_override.load(std::memory_order_relaxed) == 0;
   if (small)

@@ -350,8 +350,9 @@ B200RS_API int b200rs_set_single_tile(int on);
 
 /* Tuning/diagnostic: inputs of at most `items` items (4- or 8-byte keys with 0-, 4- or 8-byte values) are sorted by ONE
  * cooperative launch that runs every phase of the general path between grid-wide barriers (the latency path; the
- * reference uses programmatic dependent launch for the same regime, dispatch_radix_sort.cuh:1755-1756).  Default 2^20;
- * 0 sends everything above one tile through the general multi-kernel path. */
+ * reference uses programmatic dependent launch for the same regime, dispatch_radix_sort.cuh:1755-1756).  Default
+ * (items == ~0): up to 4 MiB of keys (2^20 4-byte / 2^19 8-byte keys, the measured break-even on B200); 0 sends
+ * everything above one tile through the general multi-kernel path. */
 B200RS_API int b200rs_set_small_max(unsigned long long items);
 
 /* Human-readable description of configuration `config_index` for (key_bytes, value_bytes); returns the number of

@@ -14,6 +14,8 @@ from oracle_lib import oracle_histogram, oracle_sort
 
 pytestmark = pytest.mark.gpu
 
+SMALL_DEFAULT = 2**64 - 1  # b200rs_set_small_max: the library's own threshold
+
 KEY_DTYPES = [np.uint8, np.int8, np.uint16, np.int16, np.float16, np.uint32, np.int32, np.float32, np.uint64, np.int64,
               np.float64]
 
@@ -25,9 +27,9 @@ def sort_path(request):
     from cccl_b200 import _native
 
     lib = _native.lib()
-    lib.b200rs_set_small_max(0 if request.param == "general" else (1 << 20))
+    lib.b200rs_set_small_max(0 if request.param == "general" else SMALL_DEFAULT)
     yield request.param
-    lib.b200rs_set_small_max(1 << 20)
+    lib.b200rs_set_small_max(SMALL_DEFAULT)
 
 
 def check_keys(k, **kw):
@@ -165,9 +167,10 @@ def test_single_tile_kernel_and_general_path_agree(kdtype):
             for kw in (dict(), dict(descending=True, api="double"), dict(begin_bit=bits // 4, end_bit=bits - 3,
                                                                           descending=True)):
                 info = check_pairs(k, v, **kw) if v is not None else check_keys(k, **kw)
-                assert (info["launches"] == 1) == (n <= cap), (n, cap, info)
+                # the single-CTA kernel needs no temp storage (1 byte, like the reference's empty layout)
+                assert (info["temp_bytes"] == 1) == (n <= cap), (n, cap, info)
                 if n <= cap:
-                    assert info["temp_bytes"] == 1
+                    assert info["launches"] == 1
                     try:
                         lib.b200rs_set_single_tile(0)
                         # without the single-CTA kernel: the one-launch cooperative kernel where it is compiled ...
@@ -180,7 +183,7 @@ def test_single_tile_kernel_and_general_path_agree(kdtype):
                         assert info3["launches"] > 1
                     finally:
                         lib.b200rs_set_single_tile(1)
-                        lib.b200rs_set_small_max(1 << 20)
+                        lib.b200rs_set_small_max(SMALL_DEFAULT)
 
 
 def test_double_buffer_selector_and_pass_parity(sort_path):

@@ -45,4 +45,4 @@ for kb, vb in ((4, 0), (4, 4), (8, 0), (8, 4), (8, 8)):
         b, lb = run(n, kb, vb, iters)
         print(f"k{kb}v{vb} 2^{log2n}: fused {a * 1000:8.1f} us ({la} launch)   general {b * 1000:8.1f} us ({lb} ops)   "
               f"ratio {b / a:5.2f}", flush=True)
-lib.b200rs_set_small_max(1 << 20)
+lib.b200rs_set_small_max(2**64 - 1)
