@@ -39,6 +39,17 @@ EXPORTS = (
     "b200rs_describe_config",
     "b200rs_timing_enable",
     "b200rs_timing_read",
+    # include/b200rs_cccl_c.h: the cccl.c.parallel names (c/parallel/include/cccl/c/radix_sort.h:63-143)
+    "cccl_device_radix_sort_build",
+    "cccl_device_radix_sort_build_ex",
+    "cccl_device_radix_sort_compile",
+    "cccl_device_radix_sort_load",
+    "cccl_device_radix_sort",
+    "cccl_device_radix_sort_link_ltoir",
+    "cccl_device_radix_sort_serialize",
+    "cccl_device_radix_sort_deserialize",
+    "cccl_device_radix_sort_cleanup",
+    "cccl_serialization_buffer_free",
 )
 
 # b200rs_allgather_fn: int (*)(void* ctx, const void* send, void* recv, size_t bytes_per_rank)

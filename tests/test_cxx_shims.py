@@ -34,7 +34,7 @@ def test_thrust_shim_declares_reference_api():
 
 
 def test_shim_programs_link_against_the_product_library():
-    for prog in ("test_cub_shim", "test_thrust_shim"):
+    for prog in ("test_cub_shim", "test_thrust_shim", "test_cccl_c"):
         path = os.path.join(BIN, prog)
         assert os.path.exists(path), f"{prog} not built: run __graft_entry__.build()"
         out = subprocess.run(["ldd", path], capture_output=True, text=True).stdout
@@ -62,7 +62,7 @@ int main() { int* d = nullptr; thrust::sort(d, d, %s); return 0; }
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("prog", ["test_cub_shim", "test_thrust_shim"])
+@pytest.mark.parametrize("prog", ["test_cub_shim", "test_thrust_shim", "test_cccl_c"])
 def test_shim_program_passes_on_gpu(prog):
     res = subprocess.run([os.path.join(BIN, prog)], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
