@@ -1,0 +1,460 @@
+// Segmented radix sort: every segment [begin[s], end[s]) of one key (and value) array sorted independently.
+//
+// Replaces cub::DeviceSegmentedRadixSort (/root/reference/cub/cub/device/device_segmented_radix_sort.cuh:86,234,
+// dispatch/dispatch_segmented_radix_sort.cuh, kernel DeviceSegmentedRadixSortKernel in
+// dispatch/kernels/kernel_segmented_radix_sort.cuh:113-300).  The reference launches one kernel per 6-bit digit pass,
+// each CTA doing upsweep + scan + downsweep of one segment, every pass a round trip through HBM whatever the segment
+// size.  Here ONE launch sorts everything, one CTA per segment:
+//   * a segment of at most one tile (5120 / 2560 / 1280 items for a dominant item size of <= 4 / 8 / 16 bytes) is read
+//     once, sorted entirely in shared memory (single_tile_sort: all 8-bit passes) and written once;
+//   * a longer segment runs its 8-bit passes inside the same CTA: per pass a histogram of the segment, a scan, then
+//     the tiles in order, each ranked with the same warp-ballot code and scattered behind running per-digit offsets
+//     (the chained scan of the unsegmented kernel degenerates to these running offsets when one CTA owns all tiles).
+//     Passes ping-pong between the output array and a scratch copy so that the input is never written and the last
+//     pass lands in the output (same rule as the unsegmented pointer API).
+// Positions outside every segment are neither read nor written (device_segmented_radix_sort.cuh:59).
+//
+// Key order: the reference's segmented kernel never inverts keys for descending sorts (it reverses the digit instead,
+// kernel_segmented_radix_sort.cuh:213-272), so the -0.0 == +0.0 rule applies in the un-inverted domain at EVERY segment
+// size -- the rule make_xform calls single_tile_rule (pinned by tests/golden/segmented/cubseg_f32_*).
+#include "../../include/b200rs.h"
+#include "single_tile.cuh"
+
+namespace b200rs
+{
+
+struct SegArgs
+{
+  const void* keys_in;
+  void* keys_out;
+  void* keys_tmp;
+  const void* vals_in;
+  void* vals_out;
+  void* vals_tmp;
+  const void* begin_offsets;
+  const void* end_offsets;
+  long long num_segments;
+  int offset_bytes; // 4 or 8 (signed or unsigned: segment lengths are differences)
+  int begin_bit;
+  int end_bit;
+  uint32_t all_ones;
+  KeyXform xf;
+};
+
+__device__ __forceinline__ long long load_offset(const void* p, long long i, int bytes)
+{
+  return bytes == 8 ? static_cast<const long long*>(p)[i] : (long long) static_cast<const unsigned int*>(p)[i];
+}
+
+// One 8-bit pass of one long segment by the calling CTA (src -> dst, both already offset to the segment).
+template <class U, int VBYTES, int IPT, bool FLOATK>
+__device__ __forceinline__ void segment_pass(
+  const U* src, U* dst, const typename value_of<VBYTES>::type* vsrc, typename value_of<VBYTES>::type* vdst,
+  const uint32_t len, const int bit, const uint32_t mask, const bool first, const bool last, const SegArgs& a,
+  const uint32_t sbase, uint32_t* s_off, uint32_t* s_excl)
+{
+  using L = SingleTileSmem<U, VBYTES, IPT>;
+  using V = typename value_of<VBYTES>::type;
+  constexpr int NW        = L::NW;
+  constexpr uint32_t TILE = L::TILE;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t s_cnt  = sbase + L::OFF_CNT;
+  const uint32_t s_misc = sbase + L::OFF_MISC;
+  const uint32_t s_keys = sbase + L::OFF_KEYS;
+  const uint32_t s_vals = sbase + L::OFF_VALS;
+  const uint32_t s_mine = s_cnt + warp * (RADIX * 2);
+  const XformT<U> xf(a.xf);
+  const U neg_zero = U(a.xf.neg_zero), pos_zero = U(a.xf.pos_zero);
+
+  // ---- digit histogram of the segment -> exclusive offsets
+  s_off[tid] = 0;
+  __syncthreads();
+  for (uint32_t base = tid & ~31u; base < len; base += ST_THREADS)
+  {
+    const uint32_t i  = base + lane;
+    const bool inside = i < len;
+    U k               = inside ? src[i] : U(0);
+    if (first)
+    {
+      k = twiddle_in(k, xf);
+    }
+    const uint32_t d  = pass_digit<FLOATK>(k, bit, mask, neg_zero, pos_zero);
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+    if (__all_sync(0xffffffffu, inside && d == d0)) // a warp of equal digits adds once
+    {
+      if (lane == 0)
+      {
+        atomicAdd(&s_off[d0], 32u);
+      }
+    }
+    else if (inside)
+    {
+      atomicAdd(&s_off[d], 1u);
+    }
+  }
+  __syncthreads();
+  {
+    const uint32_t c = s_off[tid];
+    uint32_t incl    = c;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1)
+    {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= uint32_t(s))
+      {
+        incl += up;
+      }
+    }
+    if (lane == 31)
+    {
+      sts32(s_misc + warp * 4, incl);
+    }
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+    {
+      const uint32_t ws = lds32(s_misc + w * 4);
+      before += (uint32_t(w) < warp) ? ws : 0u;
+    }
+    s_off[tid] = before + incl - c;
+  }
+  __syncthreads();
+
+  // ---- the tiles, in order
+  const uint32_t lt_mask = lanemask_lt(), gt_mask = lanemask_gt();
+  const uint32_t chunk = warp * 32 * IPT + lane;
+  for (uint32_t t0 = 0; t0 < len; t0 += TILE)
+  {
+    const uint32_t valid = (len - t0) < TILE ? (len - t0) : TILE;
+    U key[IPT];
+    V val[VBYTES > 0 ? IPT : 1];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+      const uint32_t p = chunk + i * 32;
+      U k              = p < valid ? src[t0 + p] : U(~U(0)); // padding: largest digit, last in tile order
+      if (first && p < valid)
+      {
+        k = twiddle_in(k, xf);
+      }
+      key[i] = k;
+      if (VBYTES > 0 && p < valid)
+      {
+        val[i] = vsrc[t0 + p];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NW * RADIX * 2 / 4 / ST_THREADS; ++j)
+    {
+      sts32(s_cnt + (j * ST_THREADS + tid) * 4, 0);
+    }
+    __syncthreads(); // also: the previous tile's staged items have been scattered
+    uint32_t rank[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+      const uint32_t d = pass_digit<FLOATK>(key[i], bit, mask, neg_zero, pos_zero);
+      uint32_t b, c;
+      match_digit_ballot_fma(d, a.all_ones, b, c);
+      const uint32_t before = __popc(b & c & lt_mask);
+      const uint32_t ctr    = s_mine + d * 2;
+      const uint32_t next   = ctr_ld<true>(ctr) + before + 1;
+      if ((b & c & gt_mask) == 0)
+      {
+        ctr_st<true>(ctr, next);
+      }
+      __syncwarp();
+      rank[i] = next - 1;
+    }
+    __syncthreads();
+    // per-digit totals of the tile, exclusive scan over digits, per-warp bases
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+    {
+      total += ctr_ld<true>(s_cnt + (w * RADIX + tid) * 2);
+    }
+    uint32_t incl = total;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1)
+    {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= uint32_t(s))
+      {
+        incl += up;
+      }
+    }
+    if (lane == 31)
+    {
+      sts32(s_misc + warp * 4, incl);
+    }
+    __syncthreads();
+    uint32_t excl = incl - total;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+    {
+      const uint32_t ws = lds32(s_misc + w * 4);
+      excl += (uint32_t(w) < warp) ? ws : 0u;
+    }
+    s_excl[tid] = excl;
+    {
+      uint32_t run = excl;
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+      {
+        const uint32_t addr = s_cnt + (w * RADIX + tid) * 2;
+        const uint32_t c    = ctr_ld<true>(addr);
+        ctr_st<true>(addr, run);
+        run += c;
+      }
+    }
+    __syncthreads();
+    // stage in digit order
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+    {
+      const uint32_t d = pass_digit<FLOATK>(key[i], bit, mask, neg_zero, pos_zero);
+      const uint32_t r = rank[i] + ctr_ld<true>(s_mine + d * 2);
+      sts_t<U>(s_keys + r * uint32_t(sizeof(U)), key[i]);
+      if (VBYTES > 0)
+      {
+        sts_t<V>(s_vals + r * uint32_t(sizeof(V)), val[i]);
+      }
+    }
+    __syncthreads();
+    // scatter behind the running offsets: staged position p of digit d goes to s_off[d] + (p - excl[d])
+    for (uint32_t p = tid; p < valid; p += ST_THREADS)
+    {
+      const U k        = lds_t<U>(s_keys + p * uint32_t(sizeof(U)));
+      const uint32_t d = pass_digit<FLOATK>(k, bit, mask, neg_zero, pos_zero);
+      const uint32_t o = s_off[d] + (p - s_excl[d]);
+      dst[o]           = last ? twiddle_out(k, xf) : k;
+      if (VBYTES > 0)
+      {
+        vdst[o] = lds_t<V>(s_vals + p * uint32_t(sizeof(V)));
+      }
+    }
+    __syncthreads();
+    // padding keys carry the largest digit and rank last: they are not part of its count
+    s_off[tid] += total - ((tid == mask) ? (TILE - valid) : 0u);
+    // (the barrier at the top of the next tile orders this update before the next scatter)
+  }
+  __syncthreads(); // the CTA's global stores of this pass are visible to its loads of the next
+}
+
+template <class U, int VBYTES, int IPT, bool FLOATK>
+__global__ void __launch_bounds__(ST_THREADS) segmented_sort_kernel(const SegArgs a)
+{
+  using L = SingleTileSmem<U, VBYTES, IPT>;
+  using V = typename value_of<VBYTES>::type;
+  extern __shared__ __align__(16) unsigned char seg_smem[];
+  __shared__ uint32_t s_off[RADIX];
+  __shared__ uint32_t s_excl[RADIX];
+  const uint32_t sbase = uint32_t(__cvta_generic_to_shared(seg_smem));
+  for (long long seg = blockIdx.x; seg < a.num_segments; seg += gridDim.x)
+  {
+    const long long b   = load_offset(a.begin_offsets, seg, a.offset_bytes);
+    const long long e   = load_offset(a.end_offsets, seg, a.offset_bytes);
+    const long long len = a.offset_bytes == 8 ? e - b : (long long) (int) (uint32_t(e) - uint32_t(b));
+    if (len <= 0)
+    {
+      continue;
+    }
+    const U* kin = static_cast<const U*>(a.keys_in) + b;
+    U* kout      = static_cast<U*>(a.keys_out) + b;
+    const V* vin = VBYTES > 0 ? static_cast<const V*>(a.vals_in) + b : nullptr;
+    V* vout      = VBYTES > 0 ? static_cast<V*>(a.vals_out) + b : nullptr;
+    __syncthreads(); // the previous segment's shared memory is dead
+    if (len <= (long long) L::TILE)
+    {
+      SingleTileArgs st;
+      st.keys_in   = kin;
+      st.keys_out  = kout;
+      st.vals_in   = vin;
+      st.vals_out  = vout;
+      st.num_items = uint32_t(len);
+      st.begin_bit = a.begin_bit;
+      st.end_bit   = a.end_bit;
+      st.all_ones  = a.all_ones;
+      st.xf        = a.xf;
+      single_tile_sort<U, VBYTES, IPT, FLOATK>(st, sbase);
+      continue;
+    }
+    U* ktmp      = static_cast<U*>(a.keys_tmp) + b;
+    V* vtmp      = VBYTES > 0 ? static_cast<V*>(a.vals_tmp) + b : nullptr;
+    const int passes = (a.end_bit - a.begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    if (passes == 0) // empty bit range: the segment is copied (dispatch_radix_sort.cuh:1966-1977)
+    {
+      for (long long i = threadIdx.x; i < len; i += ST_THREADS)
+      {
+        kout[i] = kin[i];
+        if (VBYTES > 0)
+        {
+          vout[i] = vin[i];
+        }
+      }
+      continue;
+    }
+    const U* src  = kin;
+    const V* vsrc = vin;
+    for (int p = 0; p < passes; ++p)
+    {
+      // never write the input; the last pass lands in the output (dispatch_radix_sort.cuh:1850-1857)
+      const bool to_out = ((passes - 1 - p) % 2) == 0;
+      U* dst            = to_out ? kout : ktmp;
+      V* vdst           = to_out ? vout : vtmp;
+      const int bit     = a.begin_bit + p * RADIX_BITS;
+      const int nbits   = (a.end_bit - bit) < RADIX_BITS ? (a.end_bit - bit) : RADIX_BITS;
+      segment_pass<U, VBYTES, IPT, FLOATK>(src, dst, vsrc, vdst, uint32_t(len), bit, (1u << nbits) - 1u, p == 0,
+                                           p == passes - 1, a, sbase, s_off, s_excl);
+      src  = dst;
+      vsrc = vdst;
+    }
+  }
+}
+
+template <class U, int VB>
+static cudaError_t launch_seg(const SegArgs& a, int sms, cudaStream_t stream)
+{
+  constexpr int IPT        = SingleTileShape<U, VB>::IPT;
+  using L                  = SingleTileSmem<U, VB, IPT>;
+  constexpr bool CAN_FLOAT = sizeof(U) >= 2;
+  auto kernel              = segmented_sort_kernel<U, VB, IPT, false>;
+  if (CAN_FLOAT && a.xf.float_mask != 0)
+  {
+    kernel = segmented_sort_kernel<U, VB, IPT, CAN_FLOAT>;
+  }
+  if (L::BYTES > 48 * 1024 - 4096)
+  {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::BYTES));
+    if (e != cudaSuccess)
+    {
+      return e;
+    }
+  }
+  // one CTA per segment; more segments than this grid are taken round-robin
+  const long long cap = (long long) sms * 64;
+  const unsigned grid = unsigned(a.num_segments < cap ? a.num_segments : cap);
+  kernel<<<grid, ST_THREADS, L::BYTES, stream>>>(a);
+  return cudaPeekAtLastError();
+}
+
+template <class U>
+static cudaError_t launch_seg_v(int value_bytes, const SegArgs& a, int sms, cudaStream_t stream)
+{
+  switch (value_bytes)
+  {
+    case 0: return launch_seg<U, 0>(a, sms, stream);
+    case 1: return launch_seg<U, 1>(a, sms, stream);
+    case 2: return launch_seg<U, 2>(a, sms, stream);
+    case 4: return launch_seg<U, 4>(a, sms, stream);
+    case 8: return launch_seg<U, 8>(a, sms, stream);
+    case 16: return launch_seg<U, 16>(a, sms, stream);
+    default: return cudaErrorNotSupported;
+  }
+}
+
+} // namespace b200rs
+
+using namespace b200rs;
+
+static size_t seg_align(size_t x)
+{
+  return (x + 255) / 256 * 256;
+}
+
+extern "C" int b200rs_segmented_sort(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  uint64_t num_segments,
+  const void* d_begin_offsets,
+  const void* d_end_offsets,
+  int offset_bytes,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  b200rs_stream_t stream_)
+{
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (temp_storage_bytes == nullptr || key_kind < 0 || key_kind > 2 || (offset_bytes != 4 && offset_bytes != 8))
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  if ((key_bytes != 1 && key_bytes != 2 && key_bytes != 4 && key_bytes != 8)
+      || (value_bytes != 0 && value_bytes != 1 && value_bytes != 2 && value_bytes != 4 && value_bytes != 8
+          && value_bytes != 16)
+      || (key_kind == 2 && key_bytes < 2))
+  {
+    return int(cudaErrorNotSupported);
+  }
+  if (begin_bit < 0 || end_bit < begin_bit || end_bit > key_bytes * 8)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  const int passes    = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+  const bool need_tmp = passes > 1 && num_items > single_tile_capacity(key_bytes, value_bytes);
+  // scratch copies for the passes of segments longer than one tile (the size query cannot know the segment sizes)
+  const size_t off_keys = 0;
+  const size_t off_vals = need_tmp ? seg_align(size_t(num_items) * key_bytes) : 0;
+  const size_t total    = need_tmp ? off_vals + seg_align(size_t(num_items) * value_bytes) + 255 : 1;
+  if (d_temp_storage == nullptr)
+  {
+    *temp_storage_bytes = total;
+    return 0;
+  }
+  if (*temp_storage_bytes < total)
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  if (num_items == 0 || num_segments == 0)
+  {
+    return 0;
+  }
+  if (d_keys_in == nullptr || d_keys_out == nullptr || d_begin_offsets == nullptr || d_end_offsets == nullptr
+      || (value_bytes > 0 && (d_values_in == nullptr || d_values_out == nullptr)))
+  {
+    return int(cudaErrorInvalidValue);
+  }
+  unsigned char* base = reinterpret_cast<unsigned char*>(seg_align(reinterpret_cast<size_t>(d_temp_storage)));
+  SegArgs a;
+  a.keys_in       = d_keys_in;
+  a.keys_out      = d_keys_out;
+  a.keys_tmp      = need_tmp ? base + off_keys : nullptr;
+  a.vals_in       = value_bytes > 0 ? d_values_in : nullptr;
+  a.vals_out      = value_bytes > 0 ? d_values_out : nullptr;
+  a.vals_tmp      = (need_tmp && value_bytes > 0) ? base + off_vals : nullptr;
+  a.begin_offsets = d_begin_offsets;
+  a.end_offsets   = d_end_offsets;
+  a.num_segments  = (long long) num_segments;
+  a.offset_bytes  = offset_bytes;
+  a.begin_bit     = begin_bit;
+  a.end_bit       = end_bit;
+  a.all_ones      = 0xffffffffu;
+  a.xf            = make_xform(key_kind, key_bytes, descending, /*single_tile_rule=*/true);
+  int dev = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess)
+  {
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (e != cudaSuccess)
+  {
+    return int(e);
+  }
+  switch (key_bytes)
+  {
+    case 1: return int(launch_seg_v<uint8_t>(value_bytes, a, sms, stream));
+    case 2: return int(launch_seg_v<uint16_t>(value_bytes, a, sms, stream));
+    case 4: return int(launch_seg_v<uint32_t>(value_bytes, a, sms, stream));
+    default: return int(launch_seg_v<uint64_t>(value_bytes, a, sms, stream));
+  }
+}

@@ -104,6 +104,38 @@ B200RS_API int b200rs_sort(
   b200rs_stream_t stream);
 
 /*
+ * Segmented sort: every segment [begin_offsets[s], end_offsets[s]) of the arrays is sorted independently, with the
+ * order, bit window and stability of b200rs_sort; items outside every segment are neither read nor written.
+ *
+ * Replaces cub::DeviceSegmentedRadixSort::SortKeys / SortPairs [Descending], pointer form
+ * (/root/reference/cub/cub/device/device_segmented_radix_sort.cuh:234,887,1531,2139; dispatch_segmented_radix_sort.cuh;
+ * kernel kernel_segmented_radix_sort.cuh:113-300).  d_begin_offsets / d_end_offsets: DEVICE arrays of num_segments
+ * integers of offset_bytes (4 or 8) bytes each; segments may be empty, leave gaps, and must not overlap; a segment holds
+ * fewer than 2^31 items.  Two-phase temp-storage query like b200rs_sort (the blob holds a scratch copy of the arrays
+ * for segments longer than one tile).  The inputs are never written; results are always in d_keys_out / d_values_out.
+ * ONE kernel launch: one CTA per segment, all digit passes inside it.
+ */
+B200RS_API int b200rs_segmented_sort(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  uint64_t num_segments,
+  const void* d_begin_offsets,
+  const void* d_end_offsets,
+  int offset_bytes,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  b200rs_stream_t stream);
+
+/*
  * In-place sort of device memory: the thrust::sort / thrust::sort_by_key front door (full key width).
  *
  * Replaces thrust::cuda_cub::__radix_sort::radix_sort + the tail of __smart_sort::smart_sort

@@ -142,11 +142,13 @@ int sort_impl(const void* keys_in,
               int value_bytes,
               int begin_bit,
               int end_bit,
-              int descending)
+              int descending,
+              int zero_rule = -1) // -1: by N like cub::DeviceRadixSort; 1 / 0: force the single-tile / onesweep rule
 {
   const U* kin = static_cast<const U*>(keys_in);
   U* kout      = static_cast<U*>(keys_out);
-  const bool single_tile_rule = n <= reference_single_tile_items(int(sizeof(U)), value_bytes);
+  const bool single_tile_rule =
+    zero_rule < 0 ? n <= reference_single_tile_items(int(sizeof(U)), value_bytes) : zero_rule != 0;
   std::vector<uint64_t> perm  = permutation<U>(kin, n, kind, begin_bit, end_bit, descending != 0, single_tile_rule);
   // catch2_radix_sort_helper.cuh:281-284, :305-309 (gather)
   for (uint64_t i = 0; i < n; ++i)
@@ -225,6 +227,39 @@ int oracle_radix_sort(
       return sort_impl<uint32_t>(keys_in, keys_out, vals_in, vals_out, n, key_kind, value_bytes, begin_bit, end_bit, descending);
     case 8:
       return sort_impl<uint64_t>(keys_in, keys_out, vals_in, vals_out, n, key_kind, value_bytes, begin_bit, end_bit, descending);
+    default:
+      return -1;
+  }
+}
+
+// One SEGMENT of cub::DeviceSegmentedRadixSort: the same order, except that the segmented kernel never inverts keys
+// for descending sorts (it reverses the digit: cub/cub/device/dispatch/kernels/kernel_segmented_radix_sort.cuh:213-272,
+// agent_radix_sort_downsweep.cuh), so the -0.0 -> +0.0 replacement happens in the un-inverted domain at EVERY segment
+// size -- the rule the unsegmented reference only shows below its single-tile size.  Pinned by
+// tests/golden/segmented/cubseg_f32_*.npz (real cub::DeviceSegmentedRadixSort outputs, short and long segments).
+int oracle_radix_sort_segment(
+  const void* keys_in,
+  void* keys_out,
+  const void* vals_in,
+  void* vals_out,
+  uint64_t n,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending)
+{
+  switch (key_bytes)
+  {
+    case 1:
+      return sort_impl<uint8_t>(keys_in, keys_out, vals_in, vals_out, n, key_kind, value_bytes, begin_bit, end_bit, descending, 1);
+    case 2:
+      return sort_impl<uint16_t>(keys_in, keys_out, vals_in, vals_out, n, key_kind, value_bytes, begin_bit, end_bit, descending, 1);
+    case 4:
+      return sort_impl<uint32_t>(keys_in, keys_out, vals_in, vals_out, n, key_kind, value_bytes, begin_bit, end_bit, descending, 1);
+    case 8:
+      return sort_impl<uint64_t>(keys_in, keys_out, vals_in, vals_out, n, key_kind, value_bytes, begin_bit, end_bit, descending, 1);
     default:
       return -1;
   }

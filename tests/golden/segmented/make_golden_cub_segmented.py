@@ -28,6 +28,10 @@ CASES = [
     ("cubseg_f32_zeros_window", np.float32, "uniform", [100, 257, -5, 1, 999], True, True, (8, 24)),
     ("cubseg_u64_large_segment", np.uint64, "entropy3", [6000, 3, -2, 2500], True, False, None),
     ("cubseg_i64_keys_only", np.int64, "uniform", [0, 17, 400, -9, 1200], False, True, (16, 48)),
+    # a FLOAT segment far above one tile, descending, on a bit window, full of +-0.0: pins which -0.0 rule the reference's
+    # segmented kernel applies to long segments (it never inverts keys: kernel_segmented_radix_sort.cuh:213-272)
+    ("cubseg_f32_large_desc_window", np.float32, "uniform", [9000, 200, -3, 6000], True, True, (8, 24)),
+    ("cubseg_f32_large_asc_window", np.float32, "uniform", [7000, 5], True, False, (8, 24)),
 ]
 
 

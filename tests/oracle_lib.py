@@ -41,6 +41,8 @@ def oracle():
         lib = ctypes.CDLL(path)
         lib.oracle_radix_sort.restype = ctypes.c_int
         lib.oracle_radix_sort.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint64] + [ctypes.c_int] * 6
+        lib.oracle_radix_sort_segment.restype = ctypes.c_int
+        lib.oracle_radix_sort_segment.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint64] + [ctypes.c_int] * 6
         lib.oracle_digit_histogram.restype = ctypes.c_int
         lib.oracle_digit_histogram.argtypes = [ctypes.c_void_p, ctypes.c_uint64] + [ctypes.c_int] * 5 + [ctypes.c_void_p]
         lib.oracle_counting_pass_u32.restype = ctypes.c_int
@@ -53,8 +55,11 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
-def oracle_sort(keys: np.ndarray, values: np.ndarray | None = None, *, descending=False, begin_bit=0, end_bit=None):
-    """CPU restatement of cub/test/catch2_radix_sort_helper.cuh:270-312 (stable, bit-window aware)."""
+def oracle_sort(keys: np.ndarray, values: np.ndarray | None = None, *, descending=False, begin_bit=0, end_bit=None,
+                segment=False):
+    """CPU restatement of cub/test/catch2_radix_sort_helper.cuh:270-312 (stable, bit-window aware).  segment=True: the
+    order of ONE segment of cub::DeviceSegmentedRadixSort (oracle_radix_sort_segment: same, with the segmented kernel's
+    -0.0 rule at every size)."""
     keys = np.ascontiguousarray(keys)
     kb = keys.dtype.itemsize
     if end_bit is None:
@@ -67,9 +72,9 @@ def oracle_sort(keys: np.ndarray, values: np.ndarray | None = None, *, descendin
         vb = values.dtype.itemsize
         assert values.shape[0] == keys.shape[0]
         vout = np.empty_like(values)
-    rc = oracle().oracle_radix_sort(
-        _ptr(keys), _ptr(kout), _ptr(values), _ptr(vout), keys.shape[0], key_kind_of(keys.dtype), kb, vb,
-        begin_bit, end_bit, int(descending))
+    fn = oracle().oracle_radix_sort_segment if segment else oracle().oracle_radix_sort
+    rc = fn(_ptr(keys), _ptr(kout), _ptr(values), _ptr(vout), keys.shape[0], key_kind_of(keys.dtype), kb, vb,
+            begin_bit, end_bit, int(descending))
     assert rc == 0
     return (kout, vout) if values is not None else kout
 
@@ -133,8 +138,9 @@ def oracle_segmented_sort(keys: np.ndarray, values, begin_offsets, end_offsets, 
         if e <= b:
             continue
         if values is None:
-            kout[b:e] = oracle_sort(keys[b:e], descending=descending, begin_bit=begin_bit, end_bit=end_bit)
+            kout[b:e] = oracle_sort(keys[b:e], descending=descending, begin_bit=begin_bit, end_bit=end_bit,
+                                    segment=True)
         else:
             kout[b:e], vout[b:e] = oracle_sort(keys[b:e], values[b:e], descending=descending, begin_bit=begin_bit,
-                                               end_bit=end_bit)
+                                               end_bit=end_bit, segment=True)
     return (kout, vout) if values is not None else kout

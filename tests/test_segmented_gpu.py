@@ -1,0 +1,142 @@
+"""GPU parity tests of the segmented sort (b200rs_segmented_sort) through the C ABI.
+
+Oracle: tests/oracle_lib.py:oracle_segmented_sort, pinned by outputs of the real cub::DeviceSegmentedRadixSort
+(tests/golden/segmented/cubseg_*.npz).  Case list follows cub/test/catch2_test_device_segmented_radix_sort_keys.cu /
+..._pairs.cu: empty segments, gaps, one-item segments, segments around and far above one tile, descending, bit windows,
++-0.0, every key width, offsets of both widths."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cccl_b200 import _native
+from gen import V16, make_keys, make_values
+from gpu_util import assert_same_bits, to_dev, to_host
+from oracle_lib import key_kind_of, oracle_segmented_sort
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def gpu_segmented_sort(keys, values, begins, ends, *, descending=False, begin_bit=0, end_bit=None, offset_dtype=np.int64):
+    lib = _native.lib()
+    n, kdt = keys.shape[0], keys.dtype
+    kb = kdt.itemsize
+    vb = values.dtype.itemsize if values is not None else 0
+    end_bit = kb * 8 if end_bit is None else end_bit
+    d_k, d_v = to_dev(keys), to_dev(values)
+    # the output starts as a copy of the input: items outside every segment must come back untouched
+    d_ko = d_k.clone()
+    d_vo = d_v.clone() if values is not None else None
+    d_b, d_e = to_dev(np.asarray(begins, dtype=offset_dtype)), to_dev(np.asarray(ends, dtype=offset_dtype))
+    p = lambda t: t.data_ptr() if t is not None and t.numel() else None
+    args = (n, len(begins), p(d_b), p(d_e), np.dtype(offset_dtype).itemsize, key_kind_of(kdt), kb, vb, begin_bit, end_bit,
+            int(bool(descending)), torch.cuda.current_stream().cuda_stream)
+    nbytes = ctypes.c_size_t(0)
+    _native.check(lib.b200rs_segmented_sort(None, ctypes.byref(nbytes), None, None, None, None, *args), "size query")
+    temp = torch.empty(nbytes.value + 300, dtype=torch.uint8, device="cuda")
+    _native.check(lib.b200rs_segmented_sort(temp.data_ptr() + 4, ctypes.byref(nbytes), p(d_k), p(d_ko), p(d_v), p(d_vo),
+                                            *args), "b200rs_segmented_sort")
+    torch.cuda.synchronize()
+    assert np.array_equal(to_host(d_k, kdt, n).view(np.uint8), keys.view(np.uint8)), "input keys clobbered"
+    gk = to_host(d_ko, kdt, n)
+    gv = to_host(d_vo, values.dtype, n) if values is not None else None
+    return gk, gv
+
+
+def layout(lengths):
+    begins, ends, pos = [], [], 0
+    for ln in lengths:
+        if ln < 0:
+            pos += -ln
+        else:
+            begins.append(pos)
+            ends.append(pos + ln)
+            pos += ln
+    return np.array(begins, dtype=np.int64), np.array(ends, dtype=np.int64), pos
+
+
+def check(keys, values, begins, ends, **kw):
+    okw = {k: v for k, v in kw.items() if k != "offset_dtype"}
+    gk, gv = gpu_segmented_sort(keys, values, begins, ends, **kw)
+    if values is None:
+        ek = oracle_segmented_sort(keys, None, begins, ends, **okw)
+        assert_same_bits(gk, ek, f"segmented keys {keys.dtype} {kw}")
+    else:
+        ek, ev = oracle_segmented_sort(keys, values, begins, ends, **okw)
+        assert_same_bits(gk, ek, f"segmented pair keys {keys.dtype} {kw}")
+        assert_same_bits(gv, ev, f"segmented pair values {keys.dtype} {kw}")
+
+
+def test_real_cub_segmented_fixtures():
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "segmented", "cubseg_*.npz")))
+    assert len(files) >= 5
+    for f in files:
+        z = np.load(f)
+        kw = dict(descending=bool(z["descending"]), begin_bit=int(z["begin_bit"]), end_bit=int(z["end_bit"]))
+        vals = z["vals_in"] if "vals_in" in z.files else None
+        gk, gv = gpu_segmented_sort(z["keys_in"], vals, z["begin_offsets"], z["end_offsets"], **kw)
+        # the reference tool leaves items outside the segments as it found them in ITS output buffer; compare the segments
+        for b, e in zip(z["begin_offsets"].tolist(), z["end_offsets"].tolist()):
+            assert_same_bits(gk[b:e], z["keys_out"][b:e], f"{os.path.basename(f)} keys [{b},{e})")
+            if vals is not None:
+                assert_same_bits(gv[b:e], z["vals_out"][b:e], f"{os.path.basename(f)} values [{b},{e})")
+
+
+@pytest.mark.parametrize("kdtype", [np.uint8, np.int16, np.float16, np.uint32, np.int32, np.float32, np.uint64, np.float64])
+@pytest.mark.parametrize("descending", [False, True])
+def test_segment_shapes_all_key_types(kdtype, descending):
+    lengths = [0, 1, 2, -3, 31, 32, 33, 0, 255, 1279, 1280, 1281, -1, 2560, 2561, 5119, 5120, 5121, 7000, -11, 20_011, 3]
+    begins, ends, n = layout(lengths)
+    k = make_keys("uniform", n, kdtype, seed=77)
+    if np.dtype(kdtype).kind == "f":
+        k[::5] = -0.0
+        k[::7] = 0.0
+    check(k, None, begins, ends, descending=descending)
+    check(k, make_values(n, np.uint32), begins, ends, descending=descending, offset_dtype=np.int32)
+
+
+@pytest.mark.parametrize("vdtype", [np.uint8, np.uint16, np.uint64, V16])
+def test_value_widths_and_stability(vdtype):
+    lengths = [300, 6000, 0, 14_000, -5, 1]
+    begins, ends, n = layout(lengths)
+    for kdtype in (np.uint32, np.uint64):
+        k = make_keys("few16", n, kdtype, seed=5)  # many ties inside every segment: stability is visible in the values
+        check(k, make_values(n, vdtype), begins, ends)
+        check(k, make_values(n, vdtype), begins, ends, descending=True)
+
+
+@pytest.mark.parametrize("kdtype", [np.uint32, np.float32, np.int64])
+def test_bit_windows_and_float_zeros(kdtype):
+    lengths = [100, 257, -5, 1, 999, 6001, 13_000]
+    begins, ends, n = layout(lengths)
+    bits = np.dtype(kdtype).itemsize * 8
+    k = make_keys("entropy3", n, kdtype, seed=9)
+    if np.dtype(kdtype).kind == "f":
+        k[::3] = -0.0
+        k[::4] = 0.0
+    v = make_values(n, np.uint32)
+    for b, e in ((0, bits), (8, 24), (3, bits - 5), (bits - 1, bits), (7, 7)):
+        for desc in (False, True):
+            check(k, v, begins, ends, descending=desc, begin_bit=b, end_bit=e)
+
+
+def test_many_small_segments_and_one_large():
+    rng = np.random.default_rng(3)
+    lengths = rng.integers(0, 40, size=20_000).tolist() + [1 << 20] + rng.integers(0, 3000, size=300).tolist()
+    begins, ends, n = layout(lengths)
+    k = make_keys("uniform", n, np.uint32, seed=123)
+    check(k, make_values(n, np.uint32), begins, ends)
+    k = make_keys("equal", n, np.uint64, seed=1)
+    check(k, make_values(n, np.uint32), begins, ends, descending=True)
+
+
+def test_segments_in_any_order_and_unsorted_offsets():
+    """Segments need not be listed in address order (the reference indexes them independently)."""
+    begins, ends, n = layout([5000, 70, 9000, 0, 12])
+    perm = np.array([2, 0, 4, 3, 1])
+    k = make_keys("uniform", n, np.int32, seed=4)
+    check(k, None, begins[perm], ends[perm])

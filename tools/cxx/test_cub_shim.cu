@@ -5,6 +5,7 @@
 // checked on the host against std::stable_sort over the bit-ordered key (the helper the reference tests use,
 // catch2_radix_sort_helper.cuh:174-312).  Run by tests/test_cxx_shims.py under `pytest -m gpu`; exit code 0 == pass.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstdint>
@@ -454,10 +455,103 @@ void partition_case(size_t n, int and_rounds)
   REQUIRE(ov.host() == ev);
 }
 
+// cub::DeviceSegmentedRadixSort shim: pointer + DoubleBuffer forms, keys and pairs, 32- and 64-bit offsets, gaps and
+// empty segments (documentation example of device_segmented_radix_sort.cuh:140-170 first).
+void segmented_cases()
+{
+  { // the reference's documentation example
+    std::vector<int> hk{8, 6, 7, 5, 3, 0, 9}, hv{0, 1, 2, 3, 4, 5, 6}, off{0, 3, 3, 7};
+    dev<int> k(hk), ko(hk.size()), v(hv), vo(hv.size()), o(off);
+    size_t bytes = 0;
+    REQUIRE(cub::DeviceSegmentedRadixSort::SortPairs(nullptr, bytes, k.p, ko.p, v.p, vo.p, 7, 3, o.p, o.p + 1) == cudaSuccess);
+    dev<unsigned char> temp(bytes);
+    REQUIRE(cub::DeviceSegmentedRadixSort::SortPairs(temp.p, bytes, k.p, ko.p, v.p, vo.p, 7, 3, o.p, o.p + 1) == cudaSuccess);
+    REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+    REQUIRE((ko.host() == std::vector<int>{6, 7, 8, 0, 3, 5, 9}));
+    REQUIRE((vo.host() == std::vector<int>{1, 2, 0, 5, 4, 3, 6}));
+  }
+  std::mt19937_64 rng(31);
+  const std::vector<long long> lens{0, 1, 17, 5000, 5200, 0, 40000, 3, 9000};
+  std::vector<long long> begins, ends;
+  long long pos = 0;
+  for (long long l : lens)
+  {
+    pos += 2; // a gap before every segment
+    begins.push_back(pos);
+    ends.push_back(pos + l);
+    pos += l;
+  }
+  const size_t n = size_t(pos + 5);
+  std::vector<uint64_t> hk(n);
+  std::vector<uint32_t> hv(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    hk[i] = rng() & rng() & 0xffffffffffull;
+    hv[i] = uint32_t(i);
+  }
+  for (int desc = 0; desc < 2; ++desc)
+  {
+    std::vector<uint64_t> ek(hk);
+    std::vector<uint32_t> ev(hv);
+    for (size_t s = 0; s < begins.size(); ++s)
+    {
+      std::vector<size_t> idx(size_t(ends[s] - begins[s]));
+      std::iota(idx.begin(), idx.end(), size_t(begins[s]));
+      std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return desc ? hk[a] > hk[b] : hk[a] < hk[b]; });
+      for (size_t j = 0; j < idx.size(); ++j)
+      {
+        ek[size_t(begins[s]) + j] = hk[idx[j]];
+        ev[size_t(begins[s]) + j] = hv[idx[j]];
+      }
+    }
+    dev<long long> db(begins), de(ends);
+    { // pointer form; the output starts as the input so that untouched gaps compare equal
+      dev<uint64_t> k(hk), ko(hk);
+      dev<uint32_t> v(hv), vo(hv);
+      size_t bytes = 0;
+      auto call = [&](void* t) {
+        return desc ? cub::DeviceSegmentedRadixSort::SortPairsDescending(t, bytes, k.p, ko.p, v.p, vo.p, (long long) n,
+                                                                         (long long) begins.size(), db.p, de.p)
+                    : cub::DeviceSegmentedRadixSort::SortPairs(t, bytes, k.p, ko.p, v.p, vo.p, (long long) n,
+                                                               (long long) begins.size(), db.p, de.p);
+      };
+      REQUIRE(call(nullptr) == cudaSuccess);
+      dev<unsigned char> temp(bytes);
+      REQUIRE(call(temp.p) == cudaSuccess);
+      REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+      REQUIRE(ko.host() == ek);
+      REQUIRE(vo.host() == ev);
+      REQUIRE(k.host() == hk);
+    }
+    { // DoubleBuffer form, keys only, 32-bit offsets
+      std::vector<int> b32(begins.begin(), begins.end()), e32(ends.begin(), ends.end());
+      dev<int> db32(b32), de32(e32);
+      dev<uint64_t> k0(hk), k1(hk);
+      cub::DoubleBuffer<uint64_t> dk(k0.p, k1.p);
+      size_t bytes = 0;
+      auto call = [&](void* t) {
+        return desc ? cub::DeviceSegmentedRadixSort::SortKeysDescending(t, bytes, dk, (long long) n,
+                                                                        (long long) begins.size(), db32.p, de32.p)
+                    : cub::DeviceSegmentedRadixSort::SortKeys(t, bytes, dk, (long long) n, (long long) begins.size(),
+                                                              db32.p, de32.p);
+      };
+      REQUIRE(call(nullptr) == cudaSuccess);
+      REQUIRE(dk.selector == 0);
+      dev<unsigned char> temp(bytes);
+      REQUIRE(call(temp.p) == cudaSuccess);
+      REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+      std::vector<uint64_t> got(n);
+      cudaMemcpy(got.data(), dk.Current(), n * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+      REQUIRE(got == ek);
+    }
+  }
+}
+
 int main()
 {
   cudaStream_t stream;
   cudaStreamCreate(&stream);
+  segmented_cases();
   // compute-sanitizer runs (tools/sanitize.sh) cap the problem size: racecheck is ~100x slower than native
   const char* cap_env  = getenv("B200RS_TEST_MAX_N");
   const size_t max_n   = cap_env != nullptr ? size_t(atoll(cap_env)) : ~size_t(0);
