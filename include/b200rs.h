@@ -136,6 +136,42 @@ B200RS_API int b200rs_segmented_sort(
   b200rs_stream_t stream);
 
 /*
+ * Sort of user-defined keys described as a tuple of arithmetic members, most significant first (the reference's
+ * "decomposer" keys), and of 128-bit integers (two 64-bit members).
+ *
+ * Replaces the decomposer overloads of cub::DeviceRadixSort
+ * (/root/reference/cub/cub/device/device_radix_sort.cuh:671,905,1359,1565 and their Descending / SortKeys twins;
+ * member-wise digit extraction cub/cub/block/radix_rank_sort_operations.cuh:436-527).  d_keys_in / d_keys_out: arrays of
+ * key_stride_bytes-byte items; fields[f] = {byte offset inside the item, member width 1/2/4/8, b200rs_key_kind}; members
+ * compare like b200rs_sort keys (-0.0 == +0.0 per member).  [begin_bit, end_bit) counts from the least significant bit of
+ * the LAST member over the concatenated members.  Values: any item size (value_bytes == 0: keys only).  Stable;
+ * inputs are never written; fewer than 2^32 items.  Two-phase temp-storage query like b200rs_sort.
+ */
+typedef struct b200rs_key_field
+{
+  uint32_t offset;
+  uint32_t bytes;
+  int32_t kind;
+} b200rs_key_field;
+
+B200RS_API int b200rs_sort_fields(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  int key_stride_bytes,
+  const b200rs_key_field* fields,
+  int num_fields,
+  const void* d_values_in,
+  void* d_values_out,
+  int value_bytes,
+  uint64_t num_items,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  b200rs_stream_t stream);
+
+/*
  * In-place sort of device memory: the thrust::sort / thrust::sort_by_key front door (full key width).
  *
  * Replaces thrust::cuda_cub::__radix_sort::radix_sort + the tail of __smart_sort::smart_sort

@@ -12,7 +12,9 @@
 //   SortPairsDescending  pointer :1776  DoubleBuffer :2295   env :1894 / :2398
 //   SortKeys             pointer :3034  DoubleBuffer :3644   env :3138 / :3743
 //   SortKeysDescending   pointer :4211  DoubleBuffer :4669   env :4310 / :4768
-// Not provided ("next"): the decomposer overloads for user-defined key types.
+// Decomposer overloads for user-defined key types (:671, :905, :1359, :1565 and the Descending / SortKeys twins, with and
+// without a bit window) and 128-bit integer keys go through b200rs_sort_fields: the members the decomposer returns are
+// sorted as a chain of stable passes, least significant member first (see cccl_b200/csrc/fields.cu).
 //
 // Semantics kept from the reference:
 //   * d_temp_storage == nullptr  => only temp_storage_bytes is written (device_radix_sort.cuh:300-317);
@@ -27,6 +29,8 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <cuda/std/tuple>
 
 #include <cstddef>
 #include <cstdint>
@@ -82,11 +86,105 @@ constexpr int b200rs_key_kind_of()
 {
   using K = std::remove_cv_t<KeyT>;
   static_assert(std::is_arithmetic<K>::value || b200rs_is_float16<K>::value,
-                "this drop-in covers arithmetic keys; decomposer / user-defined keys are not built (SURVEY 8f)");
+                "arithmetic keys (or pass a decomposer for a user-defined key type)");
   static_assert(sizeof(K) == 1 || sizeof(K) == 2 || sizeof(K) == 4 || sizeof(K) == 8, "key width must be 1/2/4/8");
   return (std::is_floating_point<K>::value || b200rs_is_float16<K>::value) ? B200RS_KEY_FLOAT
        : (std::is_signed<K>::value && !std::is_same<K, bool>::value) ? B200RS_KEY_INT
                                                                      : B200RS_KEY_UINT;
+}
+
+template <class ValueT>
+constexpr int b200rs_value_bytes_of();
+
+// 128-bit integer keys (reference: util_type.cuh __int128 traits): two 64-bit members, the high half first
+template <class KeyT>
+struct b200rs_is_int128
+    : std::integral_constant<bool, std::is_same<std::remove_cv_t<KeyT>, __int128>::value
+                                     || std::is_same<std::remove_cv_t<KeyT>, unsigned __int128>::value>
+{};
+
+struct b200rs_field_list
+{
+  b200rs_key_field f[16];
+  int n = 0;
+  void add(size_t offset, size_t bytes, int kind)
+  {
+    if (n < 16)
+    {
+      f[n].offset = uint32_t(offset);
+      f[n].bytes  = uint32_t(bytes);
+      f[n].kind   = kind;
+    }
+    ++n;
+  }
+};
+
+// members of KeyT the decomposer exposes: tuple of references, leftmost = most significant (device_radix_sort.cuh:620-626)
+template <class KeyT, class DecomposerT>
+inline b200rs_field_list b200rs_fields_of(DecomposerT decomposer)
+{
+  alignas(KeyT) unsigned char raw[sizeof(KeyT)] = {};
+  KeyT& probe                                   = *reinterpret_cast<KeyT*>(raw); // never read, only addressed
+  b200rs_field_list out;
+  auto members = decomposer(probe);
+  ::cuda::std::apply(
+    [&](auto&... m) {
+      (out.add(size_t(reinterpret_cast<const unsigned char*>(&m) - raw), sizeof(m),
+               b200rs_key_kind_of<std::remove_reference_t<decltype(m)>>()),
+       ...);
+    },
+    members);
+  return out;
+}
+template <class KeyT>
+inline b200rs_field_list b200rs_fields_of_int128()
+{
+  b200rs_field_list out;
+  out.add(8, 8, std::is_same<std::remove_cv_t<KeyT>, __int128>::value ? B200RS_KEY_INT : B200RS_KEY_UINT);
+  out.add(0, 8, B200RS_KEY_UINT);
+  return out;
+}
+
+template <class KeyT, class ValueT>
+inline cudaError_t b200rs_fields_sort(
+  void* d_temp_storage, size_t& temp_storage_bytes, const KeyT* d_keys_in, KeyT* d_keys_out, const ValueT* d_values_in,
+  ValueT* d_values_out, unsigned long long num_items, const b200rs_field_list& fields, int begin_bit, int end_bit,
+  bool descending, cudaStream_t stream)
+{
+  if (fields.n > 16)
+  {
+    return cudaErrorNotSupported;
+  }
+  int total_bits = 0;
+  for (int i = 0; i < fields.n; ++i)
+  {
+    total_bits += int(fields.f[i].bytes) * 8;
+  }
+  return static_cast<cudaError_t>(b200rs_sort_fields(
+    d_temp_storage, &temp_storage_bytes, d_keys_in, d_keys_out, int(sizeof(KeyT)), fields.f, fields.n, d_values_in,
+    d_values_out, b200rs_value_bytes_of<ValueT>(), num_items, begin_bit, end_bit < 0 ? total_bits : end_bit,
+    descending ? 1 : 0, reinterpret_cast<b200rs_stream_t>(stream)));
+}
+
+template <class KeyT, class ValueT>
+inline cudaError_t b200rs_fields_sort_db(
+  void* d_temp_storage, size_t& temp_storage_bytes, DoubleBuffer<KeyT>& d_keys, DoubleBuffer<ValueT>* d_values,
+  unsigned long long num_items, const b200rs_field_list& fields, int begin_bit, int end_bit, bool descending,
+  cudaStream_t stream)
+{
+  const cudaError_t e = b200rs_fields_sort<KeyT, ValueT>(
+    d_temp_storage, temp_storage_bytes, d_keys.Current(), d_keys.Alternate(),
+    d_values != nullptr ? d_values->Current() : nullptr, d_values != nullptr ? d_values->Alternate() : nullptr, num_items,
+    fields, begin_bit, end_bit, descending, stream);
+  if (e == cudaSuccess && d_temp_storage != nullptr)
+  {
+    d_keys.selector ^= 1; // the result is gathered into the alternate buffers
+    if (d_values != nullptr)
+    {
+      d_values->selector ^= 1;
+    }
+  }
+  return e;
 }
 template <class ValueT>
 constexpr int b200rs_value_bytes_of()
@@ -108,6 +206,13 @@ inline cudaError_t b200rs_pointer_sort(
   bool descending,
   cudaStream_t stream)
 {
+  if constexpr (b200rs_is_int128<KeyT>::value)
+  {
+    return b200rs_fields_sort<KeyT, ValueT>(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in,
+                                            d_values_out, num_items, b200rs_fields_of_int128<KeyT>(), begin_bit, end_bit,
+                                            descending, stream);
+  }
+  else
   return static_cast<cudaError_t>(b200rs_sort(
     d_temp_storage,
     &temp_storage_bytes,
@@ -139,6 +244,13 @@ inline cudaError_t b200rs_double_buffer_sort(
   bool descending,
   cudaStream_t stream)
 {
+  if constexpr (b200rs_is_int128<KeyT>::value)
+  {
+    return b200rs_fields_sort_db<KeyT, ValueT>(d_temp_storage, temp_storage_bytes, d_keys, d_values, num_items,
+                                               b200rs_fields_of_int128<KeyT>(), begin_bit, end_bit, descending, stream);
+  }
+  else
+  {
   int selector = 0;
   const int rc = b200rs_sort(
     d_temp_storage,
@@ -166,6 +278,7 @@ inline cudaError_t b200rs_double_buffer_sort(
     }
   }
   return static_cast<cudaError_t>(rc);
+  }
 }
 } // namespace detail
 
@@ -458,6 +571,96 @@ struct DeviceRadixSort
       return SortKeysDescending(t, b, d_keys, num_items, begin_bit, end_bit, s);
     });
   }
+
+  // ------------------------------------------------------------------ decomposer overloads (user-defined key types)
+  // reference: device_radix_sort.cuh:671 / :905 (SortPairs), :1359 / :1565 (DoubleBuffer) and the Descending / SortKeys
+  // twins; DecomposerT: cuda::std::tuple<ArithmeticTs&...> operator()(KeyT&), leftmost member most significant
+#define B200RS_DECOMPOSER_OVERLOADS(PAIRS_NAME, KEYS_NAME, DESC)                                                        \
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename DecomposerT,                                  \
+            std::enable_if_t<!std::is_convertible<DecomposerT, int>::value, int> = 0>                                  \
+  static cudaError_t PAIRS_NAME(void* d_temp_storage, size_t& temp_storage_bytes, const KeyT* d_keys_in,               \
+                                KeyT* d_keys_out, const ValueT* d_values_in, ValueT* d_values_out, NumItemsT num_items, \
+                                DecomposerT decomposer, cudaStream_t stream = nullptr)                                 \
+  {                                                                                                                    \
+    return detail::b200rs_fields_sort<KeyT, ValueT>(                                                                   \
+      d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in, d_values_out,                            \
+      static_cast<unsigned long long>(num_items), detail::b200rs_fields_of<KeyT>(decomposer), 0, -1, DESC, stream);     \
+  }                                                                                                                    \
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename DecomposerT,                                  \
+            std::enable_if_t<!std::is_convertible<DecomposerT, int>::value, int> = 0>                                  \
+  static cudaError_t PAIRS_NAME(void* d_temp_storage, size_t& temp_storage_bytes, const KeyT* d_keys_in,               \
+                                KeyT* d_keys_out, const ValueT* d_values_in, ValueT* d_values_out, NumItemsT num_items, \
+                                DecomposerT decomposer, int begin_bit, int end_bit, cudaStream_t stream = nullptr)     \
+  {                                                                                                                    \
+    return detail::b200rs_fields_sort<KeyT, ValueT>(                                                                   \
+      d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in, d_values_out,                            \
+      static_cast<unsigned long long>(num_items), detail::b200rs_fields_of<KeyT>(decomposer), begin_bit, end_bit, DESC, \
+      stream);                                                                                                         \
+  }                                                                                                                    \
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename DecomposerT,                                  \
+            std::enable_if_t<!std::is_convertible<DecomposerT, int>::value, int> = 0>                                  \
+  static cudaError_t PAIRS_NAME(void* d_temp_storage, size_t& temp_storage_bytes, DoubleBuffer<KeyT>& d_keys,          \
+                                DoubleBuffer<ValueT>& d_values, NumItemsT num_items, DecomposerT decomposer,           \
+                                cudaStream_t stream = nullptr)                                                         \
+  {                                                                                                                    \
+    return detail::b200rs_fields_sort_db<KeyT, ValueT>(d_temp_storage, temp_storage_bytes, d_keys, &d_values,          \
+                                                       static_cast<unsigned long long>(num_items),                     \
+                                                       detail::b200rs_fields_of<KeyT>(decomposer), 0, -1, DESC, stream); \
+  }                                                                                                                    \
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename DecomposerT,                                  \
+            std::enable_if_t<!std::is_convertible<DecomposerT, int>::value, int> = 0>                                  \
+  static cudaError_t PAIRS_NAME(void* d_temp_storage, size_t& temp_storage_bytes, DoubleBuffer<KeyT>& d_keys,          \
+                                DoubleBuffer<ValueT>& d_values, NumItemsT num_items, DecomposerT decomposer,           \
+                                int begin_bit, int end_bit, cudaStream_t stream = nullptr)                             \
+  {                                                                                                                    \
+    return detail::b200rs_fields_sort_db<KeyT, ValueT>(                                                                \
+      d_temp_storage, temp_storage_bytes, d_keys, &d_values, static_cast<unsigned long long>(num_items),               \
+      detail::b200rs_fields_of<KeyT>(decomposer), begin_bit, end_bit, DESC, stream);                                   \
+  }                                                                                                                    \
+  template <typename KeyT, typename NumItemsT, typename DecomposerT,                                                   \
+            std::enable_if_t<!std::is_convertible<DecomposerT, int>::value, int> = 0>                                  \
+  static cudaError_t KEYS_NAME(void* d_temp_storage, size_t& temp_storage_bytes, const KeyT* d_keys_in,                \
+                               KeyT* d_keys_out, NumItemsT num_items, DecomposerT decomposer,                          \
+                               cudaStream_t stream = nullptr)                                                          \
+  {                                                                                                                    \
+    return detail::b200rs_fields_sort<KeyT, NullType>(                                                                 \
+      d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, nullptr, nullptr,                                     \
+      static_cast<unsigned long long>(num_items), detail::b200rs_fields_of<KeyT>(decomposer), 0, -1, DESC, stream);     \
+  }                                                                                                                    \
+  template <typename KeyT, typename NumItemsT, typename DecomposerT,                                                   \
+            std::enable_if_t<!std::is_convertible<DecomposerT, int>::value, int> = 0>                                  \
+  static cudaError_t KEYS_NAME(void* d_temp_storage, size_t& temp_storage_bytes, const KeyT* d_keys_in,                \
+                               KeyT* d_keys_out, NumItemsT num_items, DecomposerT decomposer, int begin_bit,           \
+                               int end_bit, cudaStream_t stream = nullptr)                                             \
+  {                                                                                                                    \
+    return detail::b200rs_fields_sort<KeyT, NullType>(                                                                 \
+      d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, nullptr, nullptr,                                     \
+      static_cast<unsigned long long>(num_items), detail::b200rs_fields_of<KeyT>(decomposer), begin_bit, end_bit, DESC, \
+      stream);                                                                                                         \
+  }                                                                                                                    \
+  template <typename KeyT, typename NumItemsT, typename DecomposerT,                                                   \
+            std::enable_if_t<!std::is_convertible<DecomposerT, int>::value, int> = 0>                                  \
+  static cudaError_t KEYS_NAME(void* d_temp_storage, size_t& temp_storage_bytes, DoubleBuffer<KeyT>& d_keys,           \
+                               NumItemsT num_items, DecomposerT decomposer, cudaStream_t stream = nullptr)             \
+  {                                                                                                                    \
+    return detail::b200rs_fields_sort_db<KeyT, NullType>(d_temp_storage, temp_storage_bytes, d_keys, nullptr,          \
+                                                         static_cast<unsigned long long>(num_items),                   \
+                                                         detail::b200rs_fields_of<KeyT>(decomposer), 0, -1, DESC,      \
+                                                         stream);                                                      \
+  }                                                                                                                    \
+  template <typename KeyT, typename NumItemsT, typename DecomposerT,                                                   \
+            std::enable_if_t<!std::is_convertible<DecomposerT, int>::value, int> = 0>                                  \
+  static cudaError_t KEYS_NAME(void* d_temp_storage, size_t& temp_storage_bytes, DoubleBuffer<KeyT>& d_keys,           \
+                               NumItemsT num_items, DecomposerT decomposer, int begin_bit, int end_bit,                \
+                               cudaStream_t stream = nullptr)                                                          \
+  {                                                                                                                    \
+    return detail::b200rs_fields_sort_db<KeyT, NullType>(                                                              \
+      d_temp_storage, temp_storage_bytes, d_keys, nullptr, static_cast<unsigned long long>(num_items),                 \
+      detail::b200rs_fields_of<KeyT>(decomposer), begin_bit, end_bit, DESC, stream);                                   \
+  }
+  B200RS_DECOMPOSER_OVERLOADS(SortPairs, SortKeys, false)
+  B200RS_DECOMPOSER_OVERLOADS(SortPairsDescending, SortKeysDescending, true)
+#undef B200RS_DECOMPOSER_OVERLOADS
 };
 
 } // namespace cub

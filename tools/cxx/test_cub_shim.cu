@@ -455,6 +455,179 @@ void partition_case(size_t n, int and_rounds)
   REQUIRE(ov.host() == ev);
 }
 
+// Decomposer overloads (user-defined keys) and 128-bit keys.  Golden vectors: the reference's documentation examples,
+// /root/reference/cub/test/catch2_test_device_radix_sort_custom.cu:479-700 (custom_t {float f; int unused; long long lli}).
+struct custom_t
+{
+  float f;
+  int unused;
+  long long int lli;
+  custom_t() = default;
+  custom_t(float f_, long long int lli_)
+      : f(f_)
+      , unused(42)
+      , lli(lli_)
+  {}
+};
+struct decomposer_t
+{
+  __host__ __device__ cuda::std::tuple<float&, long long int&> operator()(custom_t& key) const
+  {
+    return {key.f, key.lli};
+  }
+};
+static bool same_custom(const std::vector<custom_t>& a, const std::vector<custom_t>& b)
+{
+  bool ok = a.size() == b.size();
+  for (size_t i = 0; ok && i < a.size(); ++i)
+  {
+    ok = memcmp(&a[i].f, &b[i].f, 4) == 0 && a[i].lli == b[i].lli && a[i].unused == b[i].unused;
+  }
+  return ok;
+}
+
+void decomposer_cases()
+{
+  const std::vector<custom_t> in{{+2.5f, 4}, {-2.5f, 0}, {+1.1f, 3}, {+0.0f, 1}, {-0.0f, 2}, {+3.7f, 5}};
+  { // "Keys" (:513-556) and "KeysDescending" (:560-600)
+    dev<custom_t> k(in), o(in.size());
+    size_t bytes = 0;
+    REQUIRE(cub::DeviceRadixSort::SortKeys(nullptr, bytes, k.p, o.p, 6, decomposer_t{}) == cudaSuccess);
+    dev<unsigned char> temp(bytes);
+    REQUIRE(cub::DeviceRadixSort::SortKeys(temp.p, bytes, k.p, o.p, 6, decomposer_t{}) == cudaSuccess);
+    REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+    REQUIRE(same_custom(o.host(), {{-2.5f, 0}, {+0.0f, 1}, {-0.0f, 2}, {+1.1f, 3}, {+2.5f, 4}, {+3.7f, 5}}));
+    const std::vector<custom_t> in2{{+1.1f, 2}, {+2.5f, 1}, {-0.0f, 4}, {+0.0f, 3}, {-2.5f, 5}, {+3.7f, 0}};
+    dev<custom_t> k2(in2);
+    REQUIRE(cub::DeviceRadixSort::SortKeysDescending(temp.p, bytes, k2.p, o.p, 6, decomposer_t{}) == cudaSuccess);
+    REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+    REQUIRE(same_custom(o.host(), {{+3.7f, 0}, {+2.5f, 1}, {+1.1f, 2}, {-0.0f, 4}, {+0.0f, 3}, {-2.5f, 5}}));
+  }
+  { // "Pairs" (:602-650)
+    dev<custom_t> k(in), o(in.size());
+    dev<int> v(std::vector<int>{4, 0, 3, 1, 2, 5}), vo(6);
+    size_t bytes = 0;
+    REQUIRE(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k.p, o.p, v.p, vo.p, 6, decomposer_t{}) == cudaSuccess);
+    dev<unsigned char> temp(bytes);
+    REQUIRE(cub::DeviceRadixSort::SortPairs(temp.p, bytes, k.p, o.p, v.p, vo.p, 6, decomposer_t{}) == cudaSuccess);
+    REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+    REQUIRE(same_custom(o.host(), {{-2.5f, 0}, {+0.0f, 1}, {-0.0f, 2}, {+1.1f, 3}, {+2.5f, 4}, {+3.7f, 5}}));
+    REQUIRE((vo.host() == std::vector<int>{0, 1, 2, 3, 4, 5}));
+  }
+  // randomized: (float, long long) keys with many ties against a host stable sort of the tuple order; a bit window that
+  // cuts into both members; DoubleBuffer form
+  std::mt19937_64 rng(2024);
+  for (size_t n : {size_t(1000), size_t(200003)})
+  {
+    std::vector<custom_t> hk(n);
+    std::vector<uint64_t> hv(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+      hk[i] = custom_t(float(int(rng() % 13) - 6) * 0.5f, (long long) (rng() % 9) - 4);
+      hv[i] = i;
+    }
+    auto ordered_f = [](float f) {
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      if ((u & 0x7fffffffu) == 0) { u = 0; }
+      return (u & 0x80000000u) ? ~u : (u ^ 0x80000000u);
+    };
+    auto ordered_l = [](long long v) { return uint64_t(v) ^ 0x8000000000000000ull; };
+    for (int variant = 0; variant < 3; ++variant)
+    {
+      const bool desc = variant == 1;
+      const int b = variant == 2 ? 60 : 0, e = variant == 2 ? 70 : 96; // window: top 4 bits of lli + low 6 bits of f
+      auto keybits = [&](const custom_t& c) { // 96-bit concatenation f:lli restricted to [b, e)
+        unsigned __int128 x = ((unsigned __int128) ordered_f(c.f) << 64) | ordered_l(c.lli);
+        x >>= b;
+        const unsigned __int128 mask = (e - b) == 128 ? ~(unsigned __int128) 0 : (((unsigned __int128) 1 << (e - b)) - 1);
+        return x & mask;
+      };
+      std::vector<size_t> order(n);
+      std::iota(order.begin(), order.end(), size_t(0));
+      std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t c) {
+        return desc ? keybits(hk[a]) > keybits(hk[c]) : keybits(hk[a]) < keybits(hk[c]);
+      });
+      std::vector<custom_t> ek(n);
+      std::vector<uint64_t> ev(n);
+      for (size_t i = 0; i < n; ++i)
+      {
+        ek[i] = hk[order[i]];
+        ev[i] = hv[order[i]];
+      }
+      dev<custom_t> k0(hk), k1(n);
+      dev<uint64_t> v0(hv), v1(n);
+      cub::DoubleBuffer<custom_t> dk(k0.p, k1.p);
+      cub::DoubleBuffer<uint64_t> dv(v0.p, v1.p);
+      size_t bytes = 0;
+      auto call = [&](void* t) {
+        return desc ? cub::DeviceRadixSort::SortPairsDescending(t, bytes, dk, dv, n, decomposer_t{})
+             : variant == 2 ? cub::DeviceRadixSort::SortPairs(t, bytes, dk, dv, n, decomposer_t{}, b, e)
+                            : cub::DeviceRadixSort::SortPairs(t, bytes, dk, dv, n, decomposer_t{});
+      };
+      REQUIRE(call(nullptr) == cudaSuccess);
+      dev<unsigned char> temp(bytes);
+      REQUIRE(call(temp.p) == cudaSuccess);
+      REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+      std::vector<custom_t> gk(n);
+      std::vector<uint64_t> gv(n);
+      cudaMemcpy(gk.data(), dk.Current(), n * sizeof(custom_t), cudaMemcpyDeviceToHost);
+      cudaMemcpy(gv.data(), dv.Current(), n * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+      REQUIRE(same_custom(gk, ek));
+      REQUIRE(gv == ev);
+    }
+    // 128-bit integer keys through the ordinary overloads
+    std::vector<__int128> h128(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+      h128[i] = ((__int128) (long long) (rng() % 7 - 3) << 64) | (unsigned long long) (rng() & rng());
+    }
+    std::vector<__int128> e128(h128);
+    std::stable_sort(e128.begin(), e128.end());
+    dev<__int128> k(h128), o(n);
+    size_t bytes = 0;
+    REQUIRE(cub::DeviceRadixSort::SortKeys(nullptr, bytes, k.p, o.p, n) == cudaSuccess);
+    dev<unsigned char> temp(bytes);
+    REQUIRE(cub::DeviceRadixSort::SortKeys(temp.p, bytes, k.p, o.p, n) == cudaSuccess);
+    REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+    REQUIRE(o.host() == e128);
+    std::reverse(e128.begin(), e128.end());
+    REQUIRE(cub::DeviceRadixSort::SortKeysDescending(temp.p, bytes, k.p, o.p, n) == cudaSuccess);
+    REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+    REQUIRE(o.host() == e128);
+  }
+}
+
+// The call-site contract of cuda::std::sort(policy, first, last, comp) for arithmetic keys
+// (/root/reference/libcudacxx/include/cuda/std/__pstl/cuda/sort.h:67-135): it takes the ADDRESS of
+// cub::DeviceRadixSort::SortKeys[Descending] as cudaError_t(*)(void*, size_t&, DoubleBuffer<T>&, size_t, int, int,
+// cudaStream_t), queries, sorts a DoubleBuffer{first, scratch} and copies back iff the selector moved.
+template <class T>
+void pstl_callsite_contract(bool descending)
+{
+  using radix_fn = cudaError_t (*)(void*, size_t&, cub::DoubleBuffer<T>&, size_t, int, int, cudaStream_t);
+  radix_fn fn    = descending ? static_cast<radix_fn>(cub::DeviceRadixSort::SortKeysDescending)
+                              : static_cast<radix_fn>(cub::DeviceRadixSort::SortKeys);
+  std::mt19937_64 rng(5);
+  const size_t n = 123457;
+  std::vector<T> h(n);
+  for (auto& x : h) { x = T(rng()); }
+  dev<T> first(h), scratch(n);
+  cub::DoubleBuffer<T> buffer{first.p, scratch.p};
+  size_t bytes = 0;
+  REQUIRE(fn(nullptr, bytes, buffer, n, 0, int(sizeof(T) * 8), nullptr) == cudaSuccess);
+  dev<unsigned char> temp(bytes);
+  REQUIRE(fn(temp.p, bytes, buffer, n, 0, int(sizeof(T) * 8), nullptr) == cudaSuccess);
+  if (buffer.selector != 0)
+  {
+    cudaMemcpy(first.p, buffer.Current(), n * sizeof(T), cudaMemcpyDeviceToDevice);
+  }
+  REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+  std::sort(h.begin(), h.end());
+  if (descending) { std::reverse(h.begin(), h.end()); }
+  REQUIRE(first.host() == h);
+}
+
 // cub::DeviceSegmentedRadixSort shim: pointer + DoubleBuffer forms, keys and pairs, 32- and 64-bit offsets, gaps and
 // empty segments (documentation example of device_segmented_radix_sort.cuh:140-170 first).
 void segmented_cases()
@@ -552,6 +725,9 @@ int main()
   cudaStream_t stream;
   cudaStreamCreate(&stream);
   segmented_cases();
+  decomposer_cases();
+  pstl_callsite_contract<int>(false);
+  pstl_callsite_contract<unsigned long long>(true);
   // compute-sanitizer runs (tools/sanitize.sh) cap the problem size: racecheck is ~100x slower than native
   const char* cap_env  = getenv("B200RS_TEST_MAX_N");
   const size_t max_n   = cap_env != nullptr ? size_t(atoll(cap_env)) : ~size_t(0);
