@@ -17,6 +17,7 @@ EXPORTS = (
     "b200rs_version",
     "b200rs_sort",
     "b200rs_sort_inplace",
+    "b200rs_sort_tuned",
     "b200rs_segmented_sort",
     "b200rs_sort_fields",
     "b200rs_digit_histogram",
@@ -82,6 +83,9 @@ def lib() -> ctypes.CDLL:
         l.b200rs_sort.restype = i32
         l.b200rs_sort.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, vp, vp, u64,
                                   i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(i32), vp]
+        l.b200rs_sort_tuned.restype = i32
+        l.b200rs_sort_tuned.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, vp, vp, u64,
+                                        i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(i32), vp, vp]
         l.b200rs_sort_inplace.restype = i32
         l.b200rs_sort_inplace.argtypes = [vp, vp, u64, i32, i32, i32, i32, i32, vp]
         l.b200rs_segmented_sort.restype = i32

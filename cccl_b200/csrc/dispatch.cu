@@ -100,6 +100,26 @@ static const OnesweepConfig* configs_for(int key_bytes, int value_bytes, int* co
   }
 }
 
+// Per-call tuning (b200rs_sort_tuned): consulted before the process-wide diagnostic switches; only set for the
+// duration of one call on the calling thread.
+static thread_local const b200rs_tuning* t_tuning = nullptr;
+
+static int effective_config_override()
+{
+  return (t_tuning != nullptr && t_tuning->config_index >= 0) ? t_tuning->config_index
+                                                              : g_config_override.load(std::memory_order_relaxed);
+}
+static unsigned long long effective_small_max()
+{
+  return (t_tuning != nullptr && t_tuning->small_max_items >= 0) ? (unsigned long long) t_tuning->small_max_items
+                                                                 : g_small_max.load(std::memory_order_relaxed);
+}
+static bool effective_no_single_tile()
+{
+  return (t_tuning != nullptr && t_tuning->single_tile >= 0) ? t_tuning->single_tile == 0
+                                                             : g_no_single_tile.load(std::memory_order_relaxed);
+}
+
 static const OnesweepConfig* pick_config(int key_bytes, int value_bytes)
 {
   int count                 = 0;
@@ -108,7 +128,7 @@ static const OnesweepConfig* pick_config(int key_bytes, int value_bytes)
   {
     return nullptr;
   }
-  int idx = g_config_override.load(std::memory_order_relaxed);
+  int idx = effective_config_override();
   if (idx < 0 || idx >= count)
   {
     idx = 0;
@@ -208,6 +228,34 @@ int b200rs_version(void)
 int b200rs_last_launch_count(void)
 {
   return t_last_launches;
+}
+
+int b200rs_sort_tuned(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  int is_overwrite_okay,
+  int* selector,
+  b200rs_stream_t stream,
+  const b200rs_tuning* tuning)
+{
+  const b200rs_tuning* saved = t_tuning;
+  t_tuning                   = tuning;
+  const int rc = b200rs_sort(d_temp_storage, temp_storage_bytes, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items,
+                             key_kind, key_bytes, value_bytes, begin_bit, end_bit, descending, is_overwrite_okay, selector,
+                             stream);
+  t_tuning     = saved;
+  return rc;
 }
 
 int b200rs_set_config(int config_index)
@@ -425,7 +473,7 @@ int b200rs_sort(
 
   // at most one tile: the whole sort is one launch of one CTA, no temp storage
   // (dispatch_radix_sort.cuh:1980, kernel_radix_sort.cuh:330-434)
-  if (num_items <= single_tile_capacity(key_bytes, value_bytes) && !g_no_single_tile.load(std::memory_order_relaxed))
+  if (num_items <= single_tile_capacity(key_bytes, value_bytes) && !effective_no_single_tile())
   {
     if (query)
     {
@@ -464,11 +512,10 @@ int b200rs_sort(
   // mid-size inputs: every phase of the sort in ONE cooperative launch (small.cu).  Not with a forced configuration,
   // forced 64-bit offsets or a portion override: those diagnostics are about the general path.
   const bool small = small_sort_supported(key_bytes, value_bytes) && passes <= 8
-                  && (g_small_max.load(std::memory_order_relaxed) == ~0ull
-                        ? num_items * uint64_t(key_bytes) <= SMALL_MAX_KEY_BYTES
-                        : num_items <= g_small_max.load(std::memory_order_relaxed))
-                  && plan.portions == 1
-                  && g_config_override.load(std::memory_order_relaxed) < 0 && !g_force_big.load(std::memory_order_relaxed)
+                  && (effective_small_max() == ~0ull ? num_items * uint64_t(key_bytes) <= SMALL_MAX_KEY_BYTES
+                                                     : num_items <= effective_small_max())
+                  && plan.portions == 1 && effective_config_override() < 0
+                  && !g_force_big.load(std::memory_order_relaxed)
                   && g_portion_override.load(std::memory_order_relaxed) == 0;
   if (small)
   {

@@ -104,6 +104,40 @@ B200RS_API int b200rs_sort(
   b200rs_stream_t stream);
 
 /*
+ * b200rs_sort with PER-CALL tuning -- the reference's `cuda::execution::tune(policy)` carried by the environment of the
+ * env overloads (/root/reference/cub/cub/device/device_radix_sort.cuh:200-202, detail/env_dispatch.cuh:39-77): which
+ * compiled tile configuration runs the digit passes (index into b200rs_describe_config's table), up to which size the
+ * one-launch cooperative kernel is used, whether inputs of one tile take the single-CTA kernel.  A negative field
+ * keeps the library's own choice.  tuning == NULL is b200rs_sort.  The temp-storage size may depend on the tuning: query
+ * and run with the same one.  Thread-safe (nothing process-wide is touched).
+ */
+typedef struct b200rs_tuning
+{
+  int config_index;          /* onesweep tile configuration, or -1 */
+  long long small_max_items; /* largest input for the one-launch kernel (0 = never), or -1 */
+  int single_tile;           /* 1 / 0: use / do not use the single-CTA kernel, or -1 */
+} b200rs_tuning;
+
+B200RS_API int b200rs_sort_tuned(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int begin_bit,
+  int end_bit,
+  int descending,
+  int is_overwrite_okay,
+  int* selector,
+  b200rs_stream_t stream,
+  const b200rs_tuning* tuning);
+
+/*
  * Segmented sort: every segment [begin_offsets[s], end_offsets[s]) of the arrays is sorted independently, with the
  * order, bit window and stability of b200rs_sort; items outside every segment are neither read nor written.
  *

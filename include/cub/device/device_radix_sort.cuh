@@ -192,6 +192,13 @@ constexpr int b200rs_value_bytes_of()
   return std::is_same<std::remove_cv_t<ValueT>, NullType>::value ? 0 : int(sizeof(ValueT));
 }
 
+// tuning of the env overload being executed on this thread (nullptr outside one): see stream_env below
+inline const b200rs_tuning*& b200rs_current_tuning()
+{
+  static thread_local const b200rs_tuning* cur = nullptr;
+  return cur;
+}
+
 template <class KeyT, class ValueT>
 inline cudaError_t b200rs_pointer_sort(
   void* d_temp_storage,
@@ -213,7 +220,7 @@ inline cudaError_t b200rs_pointer_sort(
                                             descending, stream);
   }
   else
-  return static_cast<cudaError_t>(b200rs_sort(
+  return static_cast<cudaError_t>(b200rs_sort_tuned(
     d_temp_storage,
     &temp_storage_bytes,
     d_keys_in,
@@ -229,7 +236,8 @@ inline cudaError_t b200rs_pointer_sort(
     descending ? 1 : 0,
     /*is_overwrite_okay=*/0,
     nullptr,
-    reinterpret_cast<b200rs_stream_t>(stream)));
+    reinterpret_cast<b200rs_stream_t>(stream),
+    b200rs_current_tuning()));
 }
 
 template <class KeyT, class ValueT>
@@ -252,7 +260,7 @@ inline cudaError_t b200rs_double_buffer_sort(
   else
   {
   int selector = 0;
-  const int rc = b200rs_sort(
+  const int rc = b200rs_sort_tuned(
     d_temp_storage,
     &temp_storage_bytes,
     d_keys.Current(),
@@ -268,7 +276,8 @@ inline cudaError_t b200rs_double_buffer_sort(
     descending ? 1 : 0,
     /*is_overwrite_okay=*/1,
     &selector,
-    reinterpret_cast<b200rs_stream_t>(stream));
+    reinterpret_cast<b200rs_stream_t>(stream),
+    b200rs_current_tuning());
   if (rc == 0 && d_temp_storage != nullptr)
   {
     d_keys.selector ^= selector; // dispatch_radix_sort.cuh:1943-1944
@@ -285,12 +294,21 @@ inline cudaError_t b200rs_double_buffer_sort(
 /// Execution environment of the env overloads: the reference takes a cuda::std::execution::env carrying a stream
 /// and a memory resource (device_radix_sort.cuh:532, detail::dispatch_with_env); this stand-alone shim carries the
 /// stream and obtains the temporary storage from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync).
+/// The reference's env may also carry `cuda::execution::tune(policy)` (device_radix_sort.cuh:200-202): here the tuning is
+/// the C ABI's b200rs_tuning (tile configuration index, one-launch threshold, single-CTA switch), applied to THIS call only.
 struct stream_env
 {
   cudaStream_t stream = nullptr;
-  stream_env()        = default;
+  b200rs_tuning tuning{-1, -1, -1};
+  bool tuned = false;
+  stream_env() = default;
   stream_env(cudaStream_t s)
       : stream(s)
+  {}
+  stream_env(cudaStream_t s, const b200rs_tuning& t)
+      : stream(s)
+      , tuning(t)
+      , tuned(true)
   {}
 };
 
@@ -299,6 +317,19 @@ namespace detail
 template <class F>
 inline cudaError_t b200rs_with_env(const stream_env& env, F&& call)
 {
+  struct scoped_tuning // the env's tuning applies to the calls made below, on this thread, and to nothing else
+  {
+    const b200rs_tuning* saved;
+    explicit scoped_tuning(const b200rs_tuning* t)
+        : saved(b200rs_current_tuning())
+    {
+      b200rs_current_tuning() = t;
+    }
+    ~scoped_tuning()
+    {
+      b200rs_current_tuning() = saved;
+    }
+  } guard(env.tuned ? &env.tuning : nullptr);
   size_t bytes    = 0;
   cudaError_t err = call(nullptr, bytes, env.stream);
   if (err != cudaSuccess)

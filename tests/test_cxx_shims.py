@@ -21,7 +21,7 @@ def test_cub_shim_declares_reference_api():
         # pointer + DoubleBuffer temp-storage overloads and the two env overloads
         assert len(re.findall(r"static cudaError_t %s\(" % name, src)) >= 4, name
     assert "struct DoubleBuffer" in src and "Current()" in src and "Alternate()" in src
-    assert "b200rs_sort(" in src  # one C-ABI call, no kernels in the header
+    assert "b200rs_sort_tuned(" in src  # one C-ABI call (b200rs_sort + the per-call tuning of the env), no kernels in the header
     assert "__global__" not in src
 
 

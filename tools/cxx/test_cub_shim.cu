@@ -720,10 +720,49 @@ void segmented_cases()
   }
 }
 
+// Per-call tuning through the env overloads (reference: cuda::execution::tune in the env, device_radix_sort.cuh:200-202):
+// every compiled tile configuration, the one-launch kernel on / off and the single-CTA kernel on / off give the same
+// result, and the launch structure follows the tuning of THAT call only.
+void tuned_env_cases()
+{
+  std::mt19937_64 rng(77);
+  for (size_t n : {size_t(3000), size_t(150000)})
+  {
+    std::vector<uint32_t> h(n);
+    for (auto& x : h) { x = uint32_t(rng()); }
+    std::vector<uint32_t> e(h);
+    std::sort(e.begin(), e.end());
+    const int configs = b200rs_describe_config(4, 0, -1, nullptr, 0);
+    REQUIRE(configs >= 2);
+    for (int cfg = -1; cfg < configs; ++cfg)
+    {
+      for (int fused = 0; fused < 2; ++fused)
+      {
+        dev<uint32_t> k(h), o(n);
+        const b200rs_tuning t{cfg, fused ? -1 : 0, fused ? -1 : 0};
+        REQUIRE(cub::DeviceRadixSort::SortKeys(k.p, o.p, n, 0, 32, cub::stream_env(nullptr, t)) == cudaSuccess);
+        const int ops = b200rs_last_launch_count();
+        REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+        REQUIRE(o.host() == e);
+        // default tuning: one launch (single-CTA kernel or the cooperative kernel); switched off, or with a forced tile
+        // configuration: memset + histogram + scan + 4 passes
+        REQUIRE((ops == 1) == (fused == 1 && (cfg < 0 || n <= 5120)));
+      }
+    }
+    // an untuned call right after is unaffected
+    dev<uint32_t> k(h), o(n);
+    REQUIRE(cub::DeviceRadixSort::SortKeys(k.p, o.p, n) == cudaSuccess);
+    REQUIRE(b200rs_last_launch_count() == 1);
+    REQUIRE(cudaDeviceSynchronize() == cudaSuccess);
+    REQUIRE(o.host() == e);
+  }
+}
+
 int main()
 {
   cudaStream_t stream;
   cudaStreamCreate(&stream);
+  tuned_env_cases();
   segmented_cases();
   decomposer_cases();
   pstl_callsite_contract<int>(false);
