@@ -137,6 +137,25 @@ int run_seg(int argc, char** argv, bool pairs)
       CK(cudaMemcpy(hv.data(), vout, n * sizeof(V), cudaMemcpyDeviceToHost));
       dump(argv[11], hv.data(), n * sizeof(V));
     }
+    // context timing for tools/segmented_bench.py: REF_SEG_ITERS=<iters> repeats the same call and prints its device time
+    if (const char* its = getenv("REF_SEG_ITERS"))
+    {
+      const int iters = atoi(its) > 0 ? atoi(its) : 1;
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0));
+      CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0));
+      for (int i = 0; i < iters; ++i)
+      {
+        CK((do_segsort<K, V>(tmp, bytes, kin, kout, vin, vout, (long long) n, (long long) segs, bo, eo, desc, b, e, pairs)));
+      }
+      CK(cudaEventRecord(e1));
+      CK(cudaDeviceSynchronize());
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      printf("{\"impl\": \"cub-3.6.0 DeviceSegmentedRadixSort (reference, same GPU)\", \"n\": %zu, \"segments\": %zu, "
+             "\"ms\": %.4f, \"temp_bytes\": %zu}\n", n, segs, ms / iters, bytes);
+    }
     return 0;
   }
   return 1;
