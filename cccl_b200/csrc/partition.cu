@@ -128,6 +128,78 @@ __global__ void __launch_bounds__(PART_THREADS) select_histogram_kernel(
         }
       }
     }
+    if (one_byte_prefix)
+    {
+      // The only round that scans every key.  Each thread tests its LOADS * VEC keys with one table look-up each, then
+      // the warp handles ALL its hits of the batch together: one vote to leave early, one warp scan + one shared atomic
+      // to reserve candidate space (instead of a ballot, a branch and an atomic per key).  Dense hits (duplicated keys)
+      // fall through to the per-key path below, which aggregates equal (row, bin) pairs.
+      int rows[LOADS * VEC];
+      unsigned int nh = 0;
+#pragma unroll
+      for (int l = 0; l < LOADS; ++l)
+      {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+        {
+          const unsigned long long i = base + ((unsigned long long) l * PART_THREADS + threadIdx.x) * VEC + j;
+          U v                        = raw[l].k[j];
+          if (is_float)
+          {
+            v = digit_view(twiddle_in(v, xf), xf);
+          }
+          const int row = (!CHECK || i < n) ? int(s_row[(unsigned int) (v >> (sizeof(U) * 8 - RADIX_BITS)) & (RADIX - 1)]) : -1;
+          rows[l * VEC + j] = row;
+          nh += row >= 0 ? 1u : 0u;
+        }
+      }
+      const unsigned int tot = __reduce_add_sync(0xffffffffu, nh);
+      if (tot == 0)
+      {
+        return;
+      }
+      if (tot < 64)
+      {
+        unsigned int incl = nh;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+          const unsigned int up = __shfl_up_sync(0xffffffffu, incl, d);
+          incl += lane >= (unsigned int) d ? up : 0u;
+        }
+        unsigned int pos = 0;
+        bool room        = false;
+        if (my_out != nullptr)
+        {
+          if (lane == 0)
+          {
+            pos = atomicAdd(&s_emitted, tot);
+          }
+          pos  = __shfl_sync(0xffffffffu, pos, 0);
+          room = (unsigned long long) pos + tot <= slice_cap;
+          if (!room && lane == 0)
+          {
+            cand_state_out[1] = 1; // overflow: later rounds scan every key
+          }
+          pos += incl - nh;
+        }
+#pragma unroll
+        for (int q = 0; q < LOADS * VEC; ++q)
+        {
+          if (rows[q] >= 0)
+          {
+            const U k = raw[q / VEC].k[q % VEC];
+            const U v = digit_view(twiddle_in(k, xf), xf);
+            atomicAdd(&sh[(unsigned int) rows[q] * RADIX + ((unsigned int) (v >> lo_shift) & (RADIX - 1))], 1u);
+            if (room)
+            {
+              my_out[pos++] = k;
+            }
+          }
+        }
+        return;
+      }
+    }
 #pragma unroll
     for (int l = 0; l < LOADS; ++l)
     {

@@ -7,8 +7,8 @@
 // size.  Here ONE launch sorts everything, one CTA per segment:
 //   * a segment of at most one tile (5120 / 2560 / 1280 items for a dominant item size of <= 4 / 8 / 16 bytes) is read
 //     once, sorted entirely in shared memory (single_tile_sort: all 8-bit passes) and written once;
-//   * a longer segment runs its 8-bit passes inside the same CTA: per pass a histogram of the segment, a scan, then
-//     the tiles in order, each ranked with the same warp-ballot code and scattered behind running per-digit offsets
+//   * a longer segment runs its 8-bit passes inside the same CTA: the digit histograms of every pass from one read of
+//     the segment, then per pass a scan and the tiles in order, each ranked with the same warp-ballot code and scattered behind running per-digit offsets
 //     (the chained scan of the unsegmented kernel degenerates to these running offsets when one CTA owns all tiles).
 //     Passes ping-pong between the output array and a scratch copy so that the input is never written and the last
 //     pass lands in the output (same rule as the unsegmented pointer API).
@@ -51,7 +51,7 @@ template <class U, int VBYTES, int IPT, bool FLOATK>
 __device__ __forceinline__ void segment_pass(
   const U* src, U* dst, const typename value_of<VBYTES>::type* vsrc, typename value_of<VBYTES>::type* vdst,
   const uint32_t len, const int bit, const uint32_t mask, const bool first, const bool last, const SegArgs& a,
-  const uint32_t sbase, uint32_t* s_off, uint32_t* s_excl)
+  const uint32_t sbase, const uint32_t* counts, uint32_t* s_off, uint32_t* s_excl)
 {
   using L = SingleTileSmem<U, VBYTES, IPT>;
   using V = typename value_of<VBYTES>::type;
@@ -66,32 +66,8 @@ __device__ __forceinline__ void segment_pass(
   const XformT<U> xf(a.xf);
   const U neg_zero = U(a.xf.neg_zero), pos_zero = U(a.xf.pos_zero);
 
-  // ---- digit histogram of the segment -> exclusive offsets
-  s_off[tid] = 0;
-  __syncthreads();
-  for (uint32_t base = tid & ~31u; base < len; base += ST_THREADS)
-  {
-    const uint32_t i  = base + lane;
-    const bool inside = i < len;
-    U k               = inside ? src[i] : U(0);
-    if (first)
-    {
-      k = twiddle_in(k, xf);
-    }
-    const uint32_t d  = pass_digit<FLOATK>(k, bit, mask, neg_zero, pos_zero);
-    const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
-    if (__all_sync(0xffffffffu, inside && d == d0)) // a warp of equal digits adds once
-    {
-      if (lane == 0)
-      {
-        atomicAdd(&s_off[d0], 32u);
-      }
-    }
-    else if (inside)
-    {
-      atomicAdd(&s_off[d], 1u);
-    }
-  }
+  // ---- this pass's digit counts (from the all-pass histogram of the segment) -> exclusive offsets
+  s_off[tid] = counts[tid];
   __syncthreads();
   {
     const uint32_t c = s_off[tid];
@@ -244,13 +220,15 @@ __device__ __forceinline__ void segment_pass(
 }
 
 template <class U, int VBYTES, int IPT, bool FLOATK>
-__global__ void __launch_bounds__(ST_THREADS) segmented_sort_kernel(const SegArgs a)
+__global__ void __launch_bounds__(ST_THREADS, 3) segmented_sort_kernel(const SegArgs a)
 {
   using L = SingleTileSmem<U, VBYTES, IPT>;
   using V = typename value_of<VBYTES>::type;
+  constexpr int MAXPASS = int(sizeof(U)); // 8-bit digits
   extern __shared__ __align__(16) unsigned char seg_smem[];
   __shared__ uint32_t s_off[RADIX];
   __shared__ uint32_t s_excl[RADIX];
+  __shared__ uint32_t s_hist[MAXPASS][RADIX]; // long segments: digit counts of every pass, from ONE read of the segment
   const uint32_t sbase = uint32_t(__cvta_generic_to_shared(seg_smem));
   for (long long seg = blockIdx.x; seg < a.num_segments; seg += gridDim.x)
   {
@@ -296,6 +274,42 @@ __global__ void __launch_bounds__(ST_THREADS) segmented_sort_kernel(const SegArg
       }
       continue;
     }
+    // digit histograms of every pass from one read of the segment (they do not depend on the item order)
+    for (int i = threadIdx.x; i < passes * RADIX; i += ST_THREADS)
+    {
+      (&s_hist[0][0])[i] = 0;
+    }
+    __syncthreads();
+    {
+      const XformT<U> xf(a.xf);
+      const U neg_zero = U(a.xf.neg_zero), pos_zero = U(a.xf.pos_zero);
+      const uint32_t lane = threadIdx.x & 31;
+      for (uint32_t base = threadIdx.x & ~31u; base < uint32_t(len); base += ST_THREADS)
+      {
+        const uint32_t i  = base + lane;
+        const bool inside = i < uint32_t(len);
+        const U k         = inside ? twiddle_in(kin[i], xf) : U(0);
+        for (int p = 0; p < passes; ++p)
+        {
+          const int bit       = a.begin_bit + p * RADIX_BITS;
+          const int nbits     = (a.end_bit - bit) < RADIX_BITS ? (a.end_bit - bit) : RADIX_BITS;
+          const uint32_t d    = pass_digit<FLOATK>(k, bit, (1u << nbits) - 1u, neg_zero, pos_zero);
+          const uint32_t d0   = __shfl_sync(0xffffffffu, d, 0);
+          if (__all_sync(0xffffffffu, inside && d == d0)) // a warp of equal digits adds once
+          {
+            if (lane == 0)
+            {
+              atomicAdd(&s_hist[p][d0], 32u);
+            }
+          }
+          else if (inside)
+          {
+            atomicAdd(&s_hist[p][d], 1u);
+          }
+        }
+      }
+    }
+    __syncthreads();
     const U* src  = kin;
     const V* vsrc = vin;
     for (int p = 0; p < passes; ++p)
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(ST_THREADS) segmented_sort_kernel(const SegArg
       const int bit     = a.begin_bit + p * RADIX_BITS;
       const int nbits   = (a.end_bit - bit) < RADIX_BITS ? (a.end_bit - bit) : RADIX_BITS;
       segment_pass<U, VBYTES, IPT, FLOATK>(src, dst, vsrc, vdst, uint32_t(len), bit, (1u << nbits) - 1u, p == 0,
-                                           p == passes - 1, a, sbase, s_off, s_excl);
+                                           p == passes - 1, a, sbase, s_hist[p], s_off, s_excl);
       src  = dst;
       vsrc = vdst;
     }
@@ -325,7 +339,7 @@ static cudaError_t launch_seg(const SegArgs& a, int sms, cudaStream_t stream)
   {
     kernel = segmented_sort_kernel<U, VB, IPT, CAN_FLOAT>;
   }
-  if (L::BYTES > 48 * 1024 - 4096)
+  if (L::BYTES > 32 * 1024) // static shared memory (offsets + all-pass histograms) comes on top
   {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::BYTES));
     if (e != cudaSuccess)
