@@ -20,6 +20,7 @@ EXPORTS = (
     "b200rs_sort_tuned",
     "b200rs_segmented_sort",
     "b200rs_sort_fields",
+    "b200rs_topk",
     "b200rs_digit_histogram",
     "b200rs_splitter_ranks",
     "b200rs_select_histogram",
@@ -94,6 +95,8 @@ def lib() -> ctypes.CDLL:
         l.b200rs_sort_fields.restype = i32
         l.b200rs_sort_fields.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, i32, vp, i32, vp, vp, i32, u64, i32,
                                          i32, i32, vp]
+        l.b200rs_topk.restype = i32
+        l.b200rs_topk.argtypes = [vp, ctypes.POINTER(ctypes.c_size_t), vp, vp, vp, vp, u64, u64, i32, i32, i32, i32, vp]
         l.b200rs_digit_histogram.restype = i32
         l.b200rs_digit_histogram.argtypes = [vp, u64, i32, i32, i32, i32, i32, vp, vp]
         l.b200rs_splitter_ranks.restype = i32

@@ -262,6 +262,9 @@ struct PassArgs
   const PeerTable* peer; // bucket mode: remote destinations (device memory), or nullptr for keys_out / vals_out
   const PartitionPlan* plan; // bucket mode: splitters come from this device-side plan instead of the fields above
   int sm_count;          // SMs of the current device (grid size of the persistent kernel)
+  // floating-point keys: word the upsweep sets when the input holds a key with the bit pattern that ranks as the other
+  // zero (-0.0 for ascending sorts); while it is 0 the pass runs without the per-key zero test.  nullptr = always test.
+  const uint32_t* zero_flag = nullptr;
 };
 
 } // namespace b200rs

@@ -35,7 +35,7 @@ const OnesweepConfig* onesweep_configs_k8_vx(int value_bytes, int* count);
 
 cudaError_t launch_histogram(
   const void* keys, unsigned long long n, int key_bytes, unsigned long long* bins, int passes, int begin_bit,
-  int end_bit, const KeyXform& xf, int sm_count, cudaStream_t stream);
+  int end_bit, const KeyXform& xf, int sm_count, cudaStream_t stream, uint32_t* zero_flag = nullptr);
 cudaError_t launch_scan_bins(unsigned long long* bins, int passes, cudaStream_t stream);
 
 // whole sort in one CTA (single_tile.cu); capacity in items for the given key / value widths

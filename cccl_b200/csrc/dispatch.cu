@@ -555,7 +555,7 @@ int b200rs_sort(
   L.off_bins = off;
   off += align_up(size_t(size_portions) * passes * RADIX * sizeof(unsigned long long), 256);
   L.off_ctrs = off;
-  off += align_up(size_t(size_portions) * passes * sizeof(uint32_t), 256);
+  off += align_up((size_t(size_portions) * passes + 1) * sizeof(uint32_t), 256); // + the upsweep's zero flag
   L.off_lb0 = off;
   off += align_up(size_t(size_tiles) * RADIX * sizeof(uint32_t), 256);
   L.control_bytes = off;
@@ -580,6 +580,8 @@ int b200rs_sort(
   unsigned char* base = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<size_t>(d_temp_storage), 256));
   unsigned long long* bins = reinterpret_cast<unsigned long long*>(base + L.off_bins);
   uint32_t* ctrs           = reinterpret_cast<uint32_t*>(base + L.off_ctrs);
+  // floating-point keys: set by the upsweep when a key with the aliased zero pattern exists (PassArgs::zero_flag)
+  uint32_t* zero_flag      = key_kind == 2 ? ctrs + size_t(size_portions) * passes : nullptr;
   uint32_t* lb[2]          = {reinterpret_cast<uint32_t*>(base + L.off_lb0), reinterpret_cast<uint32_t*>(base + L.off_lb1)};
   void* keys_tmp           = need_tmp ? base + L.off_keys : nullptr;
   void* vals_tmp           = (need_tmp && value_bytes > 0) ? base + L.off_vals : nullptr;
@@ -604,7 +606,7 @@ int b200rs_sort(
     }
     // upsweep over the whole input: counts land in portion 0's bins, then become exclusive offsets
     mark_op(stream, OP_HISTOGRAM);
-    e = launch_histogram(d_keys_in, num_items, key_bytes, bins, passes, begin_bit, end_bit, xf, sms, stream);
+    e = launch_histogram(d_keys_in, num_items, key_bytes, bins, passes, begin_bit, end_bit, xf, sms, stream, zero_flag);
     if (e != cudaSuccess)
     {
       return int(e);
@@ -680,6 +682,7 @@ int b200rs_sort(
       a.peer          = nullptr;
       a.plan          = nullptr;
       a.sm_count      = sms;
+      a.zero_flag     = small ? nullptr : zero_flag;
       if (small)
       {
         small_pass[pass] = a; // (one portion) launched together below

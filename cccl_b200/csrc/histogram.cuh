@@ -42,9 +42,12 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v)
 
 // `mine` = shared-window address of this thread's replica of (pass 0, bin 0)
 template <class U, int PASSES, int REPLICAS>
-__device__ __forceinline__ void hist_accumulate(U bits, const XformT<U>& xf, uint32_t mine, int begin_bit, int end_bit)
+__device__ __forceinline__ void
+hist_accumulate(U bits, const XformT<U>& xf, uint32_t mine, int begin_bit, int end_bit, bool& saw_zero_alias)
 {
-  const U view = digit_view(twiddle_in(bits, xf), xf);
+  const U t    = twiddle_in(bits, xf);
+  const U view = digit_view(t, xf);
+  saw_zero_alias |= t == xf.neg_zero; // only meaningful (and only consumed) for floating-point keys
 #pragma unroll
   for (int p = 0; p < PASSES; ++p)
   {
@@ -66,7 +69,7 @@ __device__ __forceinline__ void hist_accumulate(U bits, const XformT<U>& xf, uin
 template <class U, int PASSES>
 __global__ void __launch_bounds__(HIST_THREADS, 1)
 histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long long* bins, int begin_bit, int end_bit,
-                 const KeyXform kx)
+                 const KeyXform kx, uint32_t* zero_flag)
 {
   using L                = HistLayout<int(sizeof(U))>;
   constexpr int REPLICAS = L::REPLICAS;
@@ -82,6 +85,7 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
   }
   __syncthreads();
   const uint32_t mine = sbase + (threadIdx.x & (REPLICAS - 1)) * 4;
+  bool saw            = false; // a key whose pattern is ranked as the other zero (floats: -0.0 / +0.0) was read
 
   // split [0,n) into a scalar head up to 16-byte alignment, a vector body and a scalar tail
   const unsigned long long addr = reinterpret_cast<unsigned long long>(keys);
@@ -97,11 +101,11 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
   {
     for (unsigned long long i = threadIdx.x; i < head; i += HIST_THREADS)
     {
-      hist_accumulate<U, PASSES, REPLICAS>(keys[i], xf, mine, begin_bit, end_bit);
+      hist_accumulate<U, PASSES, REPLICAS>(keys[i], xf, mine, begin_bit, end_bit, saw);
     }
     for (unsigned long long i = tail + threadIdx.x; i < n; i += HIST_THREADS)
     {
-      hist_accumulate<U, PASSES, REPLICAS>(keys[i], xf, mine, begin_bit, end_bit);
+      hist_accumulate<U, PASSES, REPLICAS>(keys[i], xf, mine, begin_bit, end_bit, saw);
     }
   }
 
@@ -124,7 +128,7 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
 #pragma unroll
       for (int j = 0; j < VEC; ++j)
       {
-        hist_accumulate<U, PASSES, REPLICAS>(e[j], xf, mine, begin_bit, end_bit);
+        hist_accumulate<U, PASSES, REPLICAS>(e[j], xf, mine, begin_bit, end_bit, saw);
       }
     }
   }
@@ -135,10 +139,14 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
 #pragma unroll
     for (int j = 0; j < VEC; ++j)
     {
-      hist_accumulate<U, PASSES, REPLICAS>(e[j], xf, mine, begin_bit, end_bit);
+      hist_accumulate<U, PASSES, REPLICAS>(e[j], xf, mine, begin_bit, end_bit, saw);
     }
   }
-  __syncthreads();
+  // the passes skip the per-key zero test while this word stays 0 (PassArgs::zero_flag)
+  if (__syncthreads_or(saw ? 1 : 0) != 0 && threadIdx.x == 0 && zero_flag != nullptr)
+  {
+    *zero_flag = 1u;
+  }
 
   // fold the replicas: consecutive threads read consecutive words (conflict-free), REPLICAS-wide segmented sum by shuffles
   for (int i = threadIdx.x; i < PASSES * RADIX * REPLICAS; i += HIST_THREADS)

@@ -1143,11 +1143,45 @@ __global__ void __launch_bounds__(NT, MINB) onesweep_kernel(const PassArgs a)
       sts32(sbase + L::OFF_PEER + w * 4, src[w]);
     }
   }
+  // floating-point keys: the upsweep recorded whether ANY key of the input carries the pattern that has to be ranked as
+  // the other zero; almost no input does, and then the pass runs the integer body (no compare + select per key in the
+  // rank, staging and scatter loops: 0.84 -> 0.70 ms per pass on 2^28 f32 keys).  One uniform load, issued before the
+  // barrier so that its latency overlaps the tile-id atomic.
+  bool plain = false;
+  if constexpr (FLOATK && (OPT & OPT_BUCKET) == 0)
+  {
+    if (a.zero_flag != nullptr)
+    {
+      plain = ld_relaxed_u32(a.zero_flag) == 0;
+    }
+  }
   __syncthreads();
   const uint32_t tile      = lds32(sbase + L::OFF_MISC + 32);
   const uint32_t tile_base = tile * uint32_t(TILE);
   const uint32_t valid     = min(uint32_t(TILE), a.num_items - tile_base);
-  if (valid == uint32_t(TILE))
+  if constexpr (FLOATK && (OPT & OPT_BUCKET) == 0)
+  {
+    if (plain)
+    {
+      if (valid == uint32_t(TILE))
+      {
+        onesweep_tile<U, VBYTES, NT, IPT, RANK, OPT, false, BIG, true>(a, sbase, tile, tile_base, valid);
+      }
+      else
+      {
+        onesweep_tile<U, VBYTES, NT, IPT, RANK, OPT, false, BIG, false>(a, sbase, tile, tile_base, valid);
+      }
+    }
+    else if (valid == uint32_t(TILE))
+    {
+      onesweep_tile<U, VBYTES, NT, IPT, RANK, OPT, true, BIG, true>(a, sbase, tile, tile_base, valid);
+    }
+    else
+    {
+      onesweep_tile<U, VBYTES, NT, IPT, RANK, OPT, true, BIG, false>(a, sbase, tile, tile_base, valid);
+    }
+  }
+  else if (valid == uint32_t(TILE))
   {
     onesweep_tile<U, VBYTES, NT, IPT, RANK, OPT, FLOATK, BIG, true>(a, sbase, tile, tile_base, valid);
   }

@@ -8,7 +8,7 @@ namespace b200rs
 template <class U, int PASSES>
 static cudaError_t launch_hist_p(
   const void* keys, unsigned long long n, unsigned long long* bins, int begin_bit, int end_bit, const KeyXform& xf,
-  unsigned grid, cudaStream_t stream)
+  unsigned grid, cudaStream_t stream, uint32_t* zero_flag)
 {
   using L     = HistLayout<int(sizeof(U))>;
   auto kernel = histogram_kernel<U, PASSES>;
@@ -22,14 +22,14 @@ static cudaError_t launch_hist_p(
       return e;
     }
   }
-  kernel<<<grid, HIST_THREADS, smem, stream>>>(static_cast<const U*>(keys), n, bins, begin_bit, end_bit, xf);
+  kernel<<<grid, HIST_THREADS, smem, stream>>>(static_cast<const U*>(keys), n, bins, begin_bit, end_bit, xf, zero_flag);
   return cudaPeekAtLastError();
 }
 
 template <class U>
 static cudaError_t launch_hist_t(
   const void* keys, unsigned long long n, unsigned long long* bins, int passes, int begin_bit, int end_bit,
-  const KeyXform& xf, int sm_count, cudaStream_t stream)
+  const KeyXform& xf, int sm_count, cudaStream_t stream, uint32_t* zero_flag)
 {
   constexpr unsigned long long VEC = 16 / sizeof(U);
   // persistent grid: one 1024-thread CTA per SM (it owns up to 128 KB of replicated counters), never more CTAs than work
@@ -41,32 +41,32 @@ static cudaError_t launch_hist_t(
   }
   switch (passes)
   {
-    case 1: return launch_hist_p<U, 1>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
-    case 2: return launch_hist_p<U, (sizeof(U) >= 2 ? 2 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
-    case 3: return launch_hist_p<U, (sizeof(U) >= 4 ? 3 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
-    case 4: return launch_hist_p<U, (sizeof(U) >= 4 ? 4 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
-    case 5: return launch_hist_p<U, (sizeof(U) >= 8 ? 5 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
-    case 6: return launch_hist_p<U, (sizeof(U) >= 8 ? 6 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
-    case 7: return launch_hist_p<U, (sizeof(U) >= 8 ? 7 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
-    case 8: return launch_hist_p<U, (sizeof(U) >= 8 ? 8 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream);
+    case 1: return launch_hist_p<U, 1>(keys, n, bins, begin_bit, end_bit, xf, grid, stream, zero_flag);
+    case 2: return launch_hist_p<U, (sizeof(U) >= 2 ? 2 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream, zero_flag);
+    case 3: return launch_hist_p<U, (sizeof(U) >= 4 ? 3 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream, zero_flag);
+    case 4: return launch_hist_p<U, (sizeof(U) >= 4 ? 4 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream, zero_flag);
+    case 5: return launch_hist_p<U, (sizeof(U) >= 8 ? 5 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream, zero_flag);
+    case 6: return launch_hist_p<U, (sizeof(U) >= 8 ? 6 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream, zero_flag);
+    case 7: return launch_hist_p<U, (sizeof(U) >= 8 ? 7 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream, zero_flag);
+    case 8: return launch_hist_p<U, (sizeof(U) >= 8 ? 8 : 1)>(keys, n, bins, begin_bit, end_bit, xf, grid, stream, zero_flag);
     default: return cudaErrorInvalidValue;
   }
 }
 
 cudaError_t launch_histogram(
   const void* keys, unsigned long long n, int key_bytes, unsigned long long* bins, int passes, int begin_bit,
-  int end_bit, const KeyXform& xf, int sm_count, cudaStream_t stream)
+  int end_bit, const KeyXform& xf, int sm_count, cudaStream_t stream, uint32_t* zero_flag)
 {
   switch (key_bytes)
   {
     case 1:
-      return launch_hist_t<uint8_t>(keys, n, bins, passes, begin_bit, end_bit, xf, sm_count, stream);
+      return launch_hist_t<uint8_t>(keys, n, bins, passes, begin_bit, end_bit, xf, sm_count, stream, zero_flag);
     case 2:
-      return launch_hist_t<uint16_t>(keys, n, bins, passes, begin_bit, end_bit, xf, sm_count, stream);
+      return launch_hist_t<uint16_t>(keys, n, bins, passes, begin_bit, end_bit, xf, sm_count, stream, zero_flag);
     case 4:
-      return launch_hist_t<uint32_t>(keys, n, bins, passes, begin_bit, end_bit, xf, sm_count, stream);
+      return launch_hist_t<uint32_t>(keys, n, bins, passes, begin_bit, end_bit, xf, sm_count, stream, zero_flag);
     case 8:
-      return launch_hist_t<uint64_t>(keys, n, bins, passes, begin_bit, end_bit, xf, sm_count, stream);
+      return launch_hist_t<uint64_t>(keys, n, bins, passes, begin_bit, end_bit, xf, sm_count, stream, zero_flag);
     default:
       return cudaErrorNotSupported;
   }

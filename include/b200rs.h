@@ -206,6 +206,30 @@ B200RS_API int b200rs_sort_fields(
   b200rs_stream_t stream);
 
 /*
+ * Top-K selection: the k best keys (largest != 0: the k largest, else the k smallest; -0.0 == +0.0, NaNs by bits as in
+ * b200rs_sort) and their values are written to d_keys_out / d_values_out[0 .. min(k, num_items)) in NO particular order;
+ * which keys tied with the k-th one are returned is unspecified.
+ *
+ * Replaces cub::DeviceTopK::{Max,Min}{Keys,Pairs} (/root/reference/cub/cub/device/device_topk.cuh:297,775,1238;
+ * dispatch/dispatch_topk.cuh).  Exact MSD radix select of the k-th key (the splitter selection of the multi-GPU sort with
+ * one target) + one filter pass: three reads of the keys, no sort, no host wait.  Two-phase temp-storage query.
+ */
+B200RS_API int b200rs_topk(
+  void* d_temp_storage,
+  size_t* temp_storage_bytes,
+  const void* d_keys_in,
+  void* d_keys_out,
+  const void* d_values_in,
+  void* d_values_out,
+  uint64_t num_items,
+  uint64_t k,
+  int key_kind,
+  int key_bytes,
+  int value_bytes,
+  int largest,
+  b200rs_stream_t stream);
+
+/*
  * In-place sort of device memory: the thrust::sort / thrust::sort_by_key front door (full key width).
  *
  * Replaces thrust::cuda_cub::__radix_sort::radix_sort + the tail of __smart_sort::smart_sort

@@ -35,6 +35,15 @@
 #include <cstddef>
 #include <cstdint>
 #include <type_traits>
+#include <utility>
+
+// cuda::get_stream (CCCL 3.x): lets the env overloads take any environment that carries a stream
+#if defined(__has_include)
+#  if __has_include(<cuda/__stream/get_stream.h>)
+#    include <cuda/__stream/get_stream.h>
+#    define B200RS_HAS_GET_STREAM 1
+#  endif
+#endif
 
 #include "../../b200rs.h"
 
@@ -312,8 +321,79 @@ struct stream_env
   {}
 };
 
+/// Property an execution environment may answer to carry a per-call tuning (the counterpart of the reference's
+/// `cuda::execution::tune`, device_radix_sort.cuh:200-202): `env.query(cub::b200rs_get_tuning_t{})` -> b200rs_tuning.
+struct b200rs_get_tuning_t
+{};
+
 namespace detail
 {
+// What the env overloads accept as EnvT (reference: any environment queryable with cuda::get_stream,
+// detail/env_dispatch.cuh:39-77): cub::stream_env, a raw cudaStream_t, cuda::stream_ref / anything whose .get() yields
+// a cudaStream_t, and any environment with .query(cuda::get_stream_t) (cuda::std::execution::env of CCCL 3.x carrying a
+// stream) when those headers are on the include path.  Other properties of such an environment (memory resource,
+// requirements) are not consulted: temporary storage always comes from the stream-ordered pool of the device.
+template <class E, class = void>
+struct b200rs_has_get : std::false_type
+{};
+template <class E>
+struct b200rs_has_get<E, std::enable_if_t<std::is_convertible<decltype(std::declval<const E&>().get()), cudaStream_t>::value>>
+    : std::true_type
+{};
+template <class E, class = void>
+struct b200rs_has_stream_query : std::false_type
+{};
+#ifdef B200RS_HAS_GET_STREAM
+template <class E>
+struct b200rs_has_stream_query<E, std::void_t<decltype(::cuda::get_stream(std::declval<const E&>()))>> : std::true_type
+{};
+#endif
+template <class E, class = void>
+struct b200rs_has_tuning_query : std::false_type
+{};
+template <class E>
+struct b200rs_has_tuning_query<
+  E,
+  std::enable_if_t<std::is_convertible<decltype(std::declval<const E&>().query(b200rs_get_tuning_t{})), b200rs_tuning>::value>>
+    : std::true_type
+{};
+template <class E>
+struct b200rs_is_env
+    : std::integral_constant<bool,
+                             std::is_same<E, stream_env>::value || std::is_same<E, cudaStream_t>::value
+                               || b200rs_has_get<E>::value || b200rs_has_stream_query<E>::value>
+{};
+
+template <class E>
+inline stream_env b200rs_env_view(const E& env)
+{
+  stream_env out;
+  if constexpr (std::is_same<E, stream_env>::value)
+  {
+    out = env;
+  }
+  else if constexpr (std::is_same<E, cudaStream_t>::value)
+  {
+    out.stream = env;
+  }
+  else if constexpr (b200rs_has_get<E>::value)
+  {
+    out.stream = env.get();
+  }
+#ifdef B200RS_HAS_GET_STREAM
+  else
+  {
+    out.stream = ::cuda::get_stream(env).get();
+  }
+#endif
+  if constexpr (!std::is_same<E, stream_env>::value && b200rs_has_tuning_query<E>::value)
+  {
+    out.tuning = env.query(b200rs_get_tuning_t{});
+    out.tuned  = true;
+  }
+  return out;
+}
+
 template <class F>
 inline cudaError_t b200rs_with_env(const stream_env& env, F&& call)
 {
@@ -385,8 +465,8 @@ struct DeviceRadixSort
       end_bit, false, stream);
   }
 
-  template <typename KeyT, typename ValueT, typename NumItemsT,
-            std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename EnvT = stream_env,
+            std::enable_if_t<std::is_integral<NumItemsT>::value && detail::b200rs_is_env<EnvT>::value, int> = 0>
   [[nodiscard]] static cudaError_t SortPairs(
     const KeyT* d_keys_in,
     KeyT* d_keys_out,
@@ -395,24 +475,24 @@ struct DeviceRadixSort
     NumItemsT num_items,
     int begin_bit         = 0,
     int end_bit           = sizeof(KeyT) * 8,
-    const stream_env& env = {})
+    const EnvT& env = {})
   {
-    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {
       return SortPairs(t, b, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items, begin_bit, end_bit, s);
     });
   }
 
-  template <typename KeyT, typename ValueT, typename NumItemsT,
-            std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename EnvT = stream_env,
+            std::enable_if_t<std::is_integral<NumItemsT>::value && detail::b200rs_is_env<EnvT>::value, int> = 0>
   [[nodiscard]] static cudaError_t SortPairs(
     DoubleBuffer<KeyT>& d_keys,
     DoubleBuffer<ValueT>& d_values,
     NumItemsT num_items,
     int begin_bit         = 0,
     int end_bit           = sizeof(KeyT) * 8,
-    const stream_env& env = {})
+    const EnvT& env = {})
   {
-    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {
       return SortPairs(t, b, d_keys, d_values, num_items, begin_bit, end_bit, s);
     });
   }
@@ -452,8 +532,8 @@ struct DeviceRadixSort
       end_bit, true, stream);
   }
 
-  template <typename KeyT, typename ValueT, typename NumItemsT,
-            std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename EnvT = stream_env,
+            std::enable_if_t<std::is_integral<NumItemsT>::value && detail::b200rs_is_env<EnvT>::value, int> = 0>
   [[nodiscard]] static cudaError_t SortPairsDescending(
     const KeyT* d_keys_in,
     KeyT* d_keys_out,
@@ -462,25 +542,25 @@ struct DeviceRadixSort
     NumItemsT num_items,
     int begin_bit         = 0,
     int end_bit           = sizeof(KeyT) * 8,
-    const stream_env& env = {})
+    const EnvT& env = {})
   {
-    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {
       return SortPairsDescending(t, b, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items, begin_bit,
                                  end_bit, s);
     });
   }
 
-  template <typename KeyT, typename ValueT, typename NumItemsT,
-            std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename EnvT = stream_env,
+            std::enable_if_t<std::is_integral<NumItemsT>::value && detail::b200rs_is_env<EnvT>::value, int> = 0>
   [[nodiscard]] static cudaError_t SortPairsDescending(
     DoubleBuffer<KeyT>& d_keys,
     DoubleBuffer<ValueT>& d_values,
     NumItemsT num_items,
     int begin_bit         = 0,
     int end_bit           = sizeof(KeyT) * 8,
-    const stream_env& env = {})
+    const EnvT& env = {})
   {
-    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {
       return SortPairsDescending(t, b, d_keys, d_values, num_items, begin_bit, end_bit, s);
     });
   }
@@ -517,29 +597,31 @@ struct DeviceRadixSort
       end_bit, false, stream);
   }
 
-  template <typename KeyT, typename NumItemsT, std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  template <typename KeyT, typename NumItemsT, typename EnvT = stream_env,
+            std::enable_if_t<std::is_integral<NumItemsT>::value && detail::b200rs_is_env<EnvT>::value, int> = 0>
   [[nodiscard]] static cudaError_t SortKeys(
     const KeyT* d_keys_in,
     KeyT* d_keys_out,
     NumItemsT num_items,
     int begin_bit         = 0,
     int end_bit           = sizeof(KeyT) * 8,
-    const stream_env& env = {})
+    const EnvT& env = {})
   {
-    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {
       return SortKeys(t, b, d_keys_in, d_keys_out, num_items, begin_bit, end_bit, s);
     });
   }
 
-  template <typename KeyT, typename NumItemsT, std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  template <typename KeyT, typename NumItemsT, typename EnvT = stream_env,
+            std::enable_if_t<std::is_integral<NumItemsT>::value && detail::b200rs_is_env<EnvT>::value, int> = 0>
   [[nodiscard]] static cudaError_t SortKeys(
     DoubleBuffer<KeyT>& d_keys,
     NumItemsT num_items,
     int begin_bit         = 0,
     int end_bit           = sizeof(KeyT) * 8,
-    const stream_env& env = {})
+    const EnvT& env = {})
   {
-    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {
       return SortKeys(t, b, d_keys, num_items, begin_bit, end_bit, s);
     });
   }
@@ -576,29 +658,31 @@ struct DeviceRadixSort
       end_bit, true, stream);
   }
 
-  template <typename KeyT, typename NumItemsT, std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  template <typename KeyT, typename NumItemsT, typename EnvT = stream_env,
+            std::enable_if_t<std::is_integral<NumItemsT>::value && detail::b200rs_is_env<EnvT>::value, int> = 0>
   [[nodiscard]] static cudaError_t SortKeysDescending(
     const KeyT* d_keys_in,
     KeyT* d_keys_out,
     NumItemsT num_items,
     int begin_bit         = 0,
     int end_bit           = sizeof(KeyT) * 8,
-    const stream_env& env = {})
+    const EnvT& env = {})
   {
-    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {
       return SortKeysDescending(t, b, d_keys_in, d_keys_out, num_items, begin_bit, end_bit, s);
     });
   }
 
-  template <typename KeyT, typename NumItemsT, std::enable_if_t<std::is_integral<NumItemsT>::value, int> = 0>
+  template <typename KeyT, typename NumItemsT, typename EnvT = stream_env,
+            std::enable_if_t<std::is_integral<NumItemsT>::value && detail::b200rs_is_env<EnvT>::value, int> = 0>
   [[nodiscard]] static cudaError_t SortKeysDescending(
     DoubleBuffer<KeyT>& d_keys,
     NumItemsT num_items,
     int begin_bit         = 0,
     int end_bit           = sizeof(KeyT) * 8,
-    const stream_env& env = {})
+    const EnvT& env = {})
   {
-    return detail::b200rs_with_env(env, [&](void* t, size_t& b, cudaStream_t s) {
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {
       return SortKeysDescending(t, b, d_keys, num_items, begin_bit, end_bit, s);
     });
   }

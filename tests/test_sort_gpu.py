@@ -123,6 +123,44 @@ def test_signed_zeros_and_nans(dtype, sort_path):
         check_pairs(k, v, descending=desc, begin_bit=5, end_bit=np.dtype(dtype).itemsize * 8 - 1)
 
 
+@pytest.mark.parametrize("dtype", [np.float16, np.float32, np.float64])
+def test_float_zero_flag_switches_the_pass_body(dtype):
+    """The general path runs the passes without the per-key zero test unless the upsweep saw a key with the aliased zero
+    pattern (PassArgs::zero_flag): no such key, ONE such key at either end / in the last partial tile, many of them --
+    results stay bit-exact and +-0.0 keep their input order (values), in both directions, on several portions too."""
+    from cccl_b200 import _native
+
+    lib = _native.lib()
+    lib.b200rs_set_small_max(0)  # general path only: the one-launch kernel always tests
+    try:
+        n = 600_011
+        base = make_keys("uniform", n, dtype, seed=13)
+        base[base == 0] = 1.0  # start from an input with no zero of either sign
+        v = make_values(n, np.uint32)
+        variants = {"none": []}
+        variants["one_first"] = [(0, -0.0)]
+        variants["one_last"] = [(n - 1, -0.0), (5, 0.0)]
+        variants["pos_only"] = [(7, 0.0), (n - 2, 0.0)]
+        variants["many"] = [(i, -0.0 if i % 3 else 0.0) for i in range(0, n, 1001)]
+        for name, edits in variants.items():
+            k = base.copy()
+            for i, z in edits:
+                k[i] = z
+            for desc in (False, True):
+                check_pairs(k, v, descending=desc)
+                check_keys(k, descending=desc, api="double")
+                check_pairs(k, v, descending=desc, begin_bit=3, end_bit=np.dtype(dtype).itemsize * 8 - 2)
+        lib.b200rs_set_portion_items(50_000)
+        k = base.copy()
+        k[n - 3] = -0.0
+        k[n // 2] = 0.0
+        check_pairs(k, v)
+        check_pairs(k, v, descending=True)
+    finally:
+        lib.b200rs_set_portion_items(0)
+        lib.b200rs_set_small_max(SMALL_DEFAULT)
+
+
 @pytest.mark.parametrize("dist", ["entropy2", "entropy3", "entropy5", "equal", "few2", "few16", "few256", "sorted",
                                   "reverse"])
 @pytest.mark.parametrize("dtype", [np.uint32, np.uint64])

@@ -6,6 +6,9 @@
 // catch2_radix_sort_helper.cuh:174-312).  Run by tests/test_cxx_shims.py under `pytest -m gpu`; exit code 0 == pass.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
+#include <cub/device/device_topk.cuh>
+
+#include <cuda/stream_ref>
 
 #include <algorithm>
 #include <cstdint>
@@ -302,6 +305,44 @@ void env_api_goldens()
     cudaStreamDestroy(s);
     REQUIRE(error == cudaSuccess);
     REQUIRE((ko.host() == std::vector<int>{9, 8, 7, 6, 5, 3, 0}));
+  }
+  {
+    // the reference's own env examples pass a cuda::stream_ref (catch2_test_device_radix_sort_env_api.cu:236-247)
+    dev<int> ki(keys), ko(7), vi(vals), vo(7);
+    cudaStream_t s;
+    cudaStreamCreate(&s);
+    cuda::stream_ref stream_ref{s};
+    auto error = cub::DeviceRadixSort::SortPairs(ki.p, ko.p, vi.p, vo.p, static_cast<int>(keys.size()), 0, 32, stream_ref);
+    cudaStreamSynchronize(s);
+    REQUIRE(error == cudaSuccess);
+    REQUIRE((ko.host() == std::vector<int>{0, 3, 5, 6, 7, 8, 9}));
+    REQUIRE((vo.host() == std::vector<int>{5, 4, 3, 1, 2, 0, 6}));
+    // a raw stream, and a user environment answering a stream (.get()) and a tuning query
+    dev<int> k2(keys), o2(7);
+    error = cub::DeviceRadixSort::SortKeysDescending(k2.p, o2.p, 7, 0, 32, s);
+    cudaStreamSynchronize(s);
+    REQUIRE(error == cudaSuccess);
+    REQUIRE((o2.host() == std::vector<int>{9, 8, 7, 6, 5, 3, 0}));
+    struct my_env
+    {
+      cudaStream_t s;
+      cudaStream_t get() const
+      {
+        return s;
+      }
+      b200rs_tuning query(cub::b200rs_get_tuning_t) const
+      {
+        return b200rs_tuning{-1, 0, 0};
+      }
+    };
+    cub::DoubleBuffer<int> dk(k2.p, o2.p);
+    error = cub::DeviceRadixSort::SortKeys(dk, 7, 0, 32, my_env{s});
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    REQUIRE(error == cudaSuccess);
+    std::vector<int> got(7);
+    cudaMemcpy(got.data(), dk.Current(), 7 * sizeof(int), cudaMemcpyDeviceToHost);
+    REQUIRE((got == std::vector<int>{0, 3, 5, 6, 7, 8, 9}));
   }
   {
     dev<int> a(keys), b(7), va(vals), vb(7);
@@ -758,6 +799,142 @@ void tuned_env_cases()
   }
 }
 
+// cub::DeviceTopK (device_topk.cuh:297,775,1238): the K best keys in any order, any subset of the ties of the K-th key;
+// checked as the reference's own test does (catch2_test_device_topk_*.cu): sorted output == first K of the sorted input,
+// and for pairs every value (an input index) still carries its key.
+template <class K>
+void topk_case(size_t n, size_t k, bool largest, int and_rounds, bool pairs, cudaStream_t stream)
+{
+  std::mt19937_64 rng(n * 31 + k * 7 + (largest ? 1 : 0) + and_rounds);
+  std::vector<K> keys(n);
+  for (auto& x : keys)
+  {
+    uint64_t bits = rng();
+    for (int r = 1; r < and_rounds; ++r)
+    {
+      bits &= rng();
+    }
+    using U = std::conditional_t<sizeof(K) == 1, uint8_t,
+              std::conditional_t<sizeof(K) == 2, uint16_t, std::conditional_t<sizeof(K) == 4, uint32_t, uint64_t>>>;
+    U u = U(bits);
+    std::memcpy(&x, &u, sizeof(K));
+  }
+  if (std::is_floating_point<K>::value && n > 8)
+  {
+    keys[1] = K(-0.0);
+    keys[5] = K(0.0);
+  }
+  std::vector<uint32_t> vals(n);
+  std::iota(vals.begin(), vals.end(), 0u);
+  const size_t kk = std::min(k, n);
+  dev<K> ki(keys), ko(std::max<size_t>(kk, 1));
+  dev<uint32_t> vi(vals), vo(std::max<size_t>(kk, 1));
+  size_t bytes = 0;
+  cudaError_t e;
+  auto call = [&](void* t) {
+    if (pairs)
+    {
+      return largest ? cub::DeviceTopK::MaxPairs(t, bytes, ki.p, ko.p, vi.p, vo.p, n, k, stream)
+                     : cub::DeviceTopK::MinPairs(t, bytes, ki.p, ko.p, vi.p, vo.p, n, k, stream);
+    }
+    return largest ? cub::DeviceTopK::MaxKeys(t, bytes, ki.p, ko.p, n, k, stream)
+                   : cub::DeviceTopK::MinKeys(t, bytes, ki.p, ko.p, n, k, stream);
+  };
+  e = call(nullptr);
+  REQUIRE(e == cudaSuccess);
+  dev<unsigned char> temp(bytes);
+  e = call(temp.p);
+  REQUIRE(e == cudaSuccess);
+  REQUIRE(cudaStreamSynchronize(stream) == cudaSuccess);
+  // order-preserving image with -0.0 == +0.0
+  auto img = [&](K x) {
+    uint64_t b = ordered_bits(x);
+    if (std::is_floating_point<K>::value && x == K(0))
+    {
+      b = ordered_bits(K(0.0));
+    }
+    return b;
+  };
+  std::vector<uint64_t> want(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    want[i] = img(keys[i]);
+  }
+  if (largest)
+  {
+    std::sort(want.begin(), want.end(), std::greater<uint64_t>());
+  }
+  else
+  {
+    std::sort(want.begin(), want.end());
+  }
+  want.resize(kk);
+  auto got_k = ko.host();
+  auto got_v = vo.host();
+  std::vector<uint64_t> got(kk);
+  for (size_t i = 0; i < kk; ++i)
+  {
+    got[i] = img(got_k[i]);
+  }
+  if (largest)
+  {
+    std::sort(got.begin(), got.end(), std::greater<uint64_t>());
+  }
+  else
+  {
+    std::sort(got.begin(), got.end());
+  }
+  REQUIRE(got == want);
+  if (pairs)
+  {
+    std::vector<char> seen(n, 0);
+    bool ok = true;
+    for (size_t i = 0; i < kk; ++i)
+    {
+      ok = ok && got_v[i] < n && !seen[got_v[i]] && std::memcmp(&keys[got_v[i]], &got_k[i], sizeof(K)) == 0;
+      if (got_v[i] < n)
+      {
+        seen[got_v[i]] = 1;
+      }
+    }
+    REQUIRE(ok);
+  }
+}
+
+void topk_cases(cudaStream_t stream, size_t max_n)
+{
+  for (size_t n : {size_t(1), size_t(7), size_t(1000), size_t(70001), size_t((1u << 21) + 5)})
+  {
+    if (n > max_n)
+    {
+      continue;
+    }
+    for (size_t k : {size_t(1), size_t(5), size_t(100), n / 2 + 1, n, n + 3})
+    {
+      topk_case<uint32_t>(n, k, true, 1, false, stream);
+      topk_case<int32_t>(n, k, false, 1, true, stream);
+      topk_case<float>(n, k, true, 1, true, stream);
+      topk_case<uint32_t>(n, k, false, 5, true, stream); // few distinct keys: the K-th key has many ties
+      topk_case<uint64_t>(n, k, true, 1, true, stream);
+      topk_case<double>(n, k, false, 1, false, stream);
+      topk_case<int16_t>(n, k, true, 1, true, stream);
+      topk_case<uint8_t>(n, k, false, 1, false, stream);
+    }
+  }
+  // env overload owning its temp storage, k == 0 and empty input
+  std::vector<int> keys{8, 6, 7, 5, 3, 0, 9};
+  dev<int> ki(keys), ko(3);
+  REQUIRE(cub::DeviceTopK::MaxKeys(ki.p, ko.p, 7, 3, cuda::stream_ref{stream}) == cudaSuccess);
+  cudaStreamSynchronize(stream);
+  auto h = ko.host();
+  std::sort(h.begin(), h.end());
+  REQUIRE((h == std::vector<int>{7, 8, 9}));
+  size_t bytes = 0;
+  REQUIRE(cub::DeviceTopK::MinKeys(nullptr, bytes, ki.p, ko.p, 7, 0) == cudaSuccess);
+  REQUIRE(bytes >= 1);
+  REQUIRE(cub::DeviceTopK::MinKeys(ki.p, ko.p, 0, 3) == cudaSuccess);
+}
+
 int main()
 {
   cudaStream_t stream;
@@ -772,6 +949,7 @@ int main()
   const size_t max_n   = cap_env != nullptr ? size_t(atoll(cap_env)) : ~size_t(0);
   env_api_goldens();
   edge_cases();
+  topk_cases(stream, max_n);
   for (size_t n : {size_t(3000), size_t(77777)})
   {
     partition_case(n, 1);
