@@ -65,8 +65,36 @@ hist_accumulate(U bits, const XformT<U>& xf, uint32_t mine, int begin_bit, int e
   }
 }
 
+// Keys of at most 32 bits: the digit is extracted already scaled to the counter stride and merged with the replica's base
+// (one rotate + one LOP3 per digit, the pass's table selected by an immediate offset of the RED), instead of shift, mask,
+// multiply-add: 26.6 -> warp instructions per 32 keys for four digits (the kernel is ALU-bound, section 3.1 of DESIGN.md).
+// Needs the counters aligned to one pass's table (256 bins * REPLICAS * 4 bytes); the kernel aligns them itself.
+template <int OFFSET>
+__device__ __forceinline__ void red_shared_inc_at(uint32_t addr)
+{
+  asm volatile("red.shared.add.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFFSET), "r"(1u) : "memory");
+}
+
+struct HistFold
+{
+  uint32_t rot[4], msk[4]; // per pass: rotate-right amount and (digit mask << log2(stride))
+};
+
+template <int PASSES, int REPLICAS, int P = 0>
+__device__ __forceinline__ void hist_accumulate_fold(uint32_t view, uint32_t mine, const HistFold& f)
+{
+  if constexpr (P < PASSES)
+  {
+    red_shared_inc_at<P * RADIX * REPLICAS * 4>((__funnelshift_r(view, view, f.rot[P]) & f.msk[P]) | mine);
+    hist_accumulate_fold<PASSES, REPLICAS, P + 1>(view, mine, f);
+  }
+}
+
 // bins: [PASSES][256] uint64, zero on entry; accumulated with global atomics.
-template <class U, int PASSES>
+// MODE: 0 = the key transform is the identity (unsigned keys, ascending): no per-key transform at all; 1 = integer
+// transform (sign flip and / or descending inversion); 2 = floating point (sign-dependent flip, -0.0 viewed as +0.0, and
+// the aliased-zero flag for the passes).
+template <class U, int PASSES, int MODE>
 __global__ void __launch_bounds__(HIST_THREADS, 1)
 histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long long* bins, int begin_bit, int end_bit,
                  const KeyXform kx, uint32_t* zero_flag)
@@ -74,9 +102,26 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
   using L                = HistLayout<int(sizeof(U))>;
   constexpr int REPLICAS = L::REPLICAS;
   constexpr int VEC      = 16 / int(sizeof(U)); // keys per 128-bit load
+  constexpr bool FOLD         = sizeof(U) <= 4 && PASSES <= 4;
+  constexpr uint32_t PASS_TBL = RADIX * REPLICAS * 4; // bytes of one pass's replicated counters
   extern __shared__ __align__(16) unsigned char hsmem[];
-  uint32_t* h          = reinterpret_cast<uint32_t*>(hsmem);
-  const uint32_t sbase = uint32_t(__cvta_generic_to_shared(hsmem));
+  // FOLD: the tables start at the next multiple of PASS_TBL (the launcher reserves the slack)
+  const uint32_t sraw  = uint32_t(__cvta_generic_to_shared(hsmem));
+  const uint32_t sbase = FOLD ? (sraw + PASS_TBL - 1u) & ~(PASS_TBL - 1u) : sraw;
+  uint32_t* h          = reinterpret_cast<uint32_t*>(hsmem + (sbase - sraw));
+  HistFold fold;
+  if constexpr (FOLD)
+  {
+    constexpr int LOG_STRIDE = REPLICAS == 32 ? 7 : 6;
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p)
+    {
+      const int bit   = begin_bit + p * RADIX_BITS;
+      const int nbits = min(RADIX_BITS, end_bit - bit);
+      fold.rot[p]     = uint32_t(bit - LOG_STRIDE) & 31u;
+      fold.msk[p]     = ((1u << nbits) - 1u) << LOG_STRIDE;
+    }
+  }
 
   const XformT<U> xf(kx);
   for (int i = threadIdx.x; i < PASSES * RADIX * REPLICAS; i += HIST_THREADS)
@@ -86,6 +131,26 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
   __syncthreads();
   const uint32_t mine = sbase + (threadIdx.x & (REPLICAS - 1)) * 4;
   bool saw            = false; // a key whose pattern is ranked as the other zero (floats: -0.0 / +0.0) was read
+  auto accumulate = [&](U bits) {
+    if constexpr (FOLD)
+    {
+      U t = bits;
+      if constexpr (MODE >= 1)
+      {
+        t = twiddle_in(bits, xf);
+      }
+      if constexpr (MODE == 2)
+      {
+        saw |= t == xf.neg_zero;
+        t = digit_view(t, xf);
+      }
+      hist_accumulate_fold<PASSES, REPLICAS>(uint32_t(t), mine, fold);
+    }
+    else
+    {
+      hist_accumulate<U, PASSES, REPLICAS>(bits, xf, mine, begin_bit, end_bit, saw);
+    }
+  };
 
   // split [0,n) into a scalar head up to 16-byte alignment, a vector body and a scalar tail
   const unsigned long long addr = reinterpret_cast<unsigned long long>(keys);
@@ -101,11 +166,11 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
   {
     for (unsigned long long i = threadIdx.x; i < head; i += HIST_THREADS)
     {
-      hist_accumulate<U, PASSES, REPLICAS>(keys[i], xf, mine, begin_bit, end_bit, saw);
+      accumulate(keys[i]);
     }
     for (unsigned long long i = tail + threadIdx.x; i < n; i += HIST_THREADS)
     {
-      hist_accumulate<U, PASSES, REPLICAS>(keys[i], xf, mine, begin_bit, end_bit, saw);
+      accumulate(keys[i]);
     }
   }
 
@@ -128,7 +193,7 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
 #pragma unroll
       for (int j = 0; j < VEC; ++j)
       {
-        hist_accumulate<U, PASSES, REPLICAS>(e[j], xf, mine, begin_bit, end_bit, saw);
+        accumulate(e[j]);
       }
     }
   }
@@ -139,7 +204,7 @@ histogram_kernel(const U* __restrict__ keys, unsigned long long n, unsigned long
 #pragma unroll
     for (int j = 0; j < VEC; ++j)
     {
-      hist_accumulate<U, PASSES, REPLICAS>(e[j], xf, mine, begin_bit, end_bit, saw);
+      accumulate(e[j]);
     }
   }
   // the passes skip the per-key zero test while this word stays 0 (PassArgs::zero_flag)

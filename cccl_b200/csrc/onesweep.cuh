@@ -58,7 +58,9 @@ enum OnesweepOpt
   // 4-byte keys, 16-bit counters: the digit is extracted already scaled and merged with the table base (one rotate +
   // one LOP3 give the shared-memory address), and the scatter folds the staged position into a per-thread pointer
   OPT_FOLD        = 256,
-  OPT_FOLD_PTR    = 512 // with OPT_FOLD: scatter through a per-thread pointer + biased offsets instead of offset + position
+  OPT_FOLD_PTR    = 512, // with OPT_FOLD: scatter through a per-thread pointer + biased offsets instead of offset + position
+  OPT_DH_FMA      = 1024 // with OPT_FOLD: the high nibble of the digit is brought down by a multiply-high (FMA pipe)
+                         // instead of a shift (ALU pipe, the binding pipe of the rank loop)
 };
 
 template <class U, int VBYTES, int NT, int IPT, int OPT = 0>
@@ -439,13 +441,22 @@ digit_entry(uint32_t key, uint32_t rot, uint32_t scaled_mask, uint32_t base, uin
 }
 
 // match-by-ballot on the digit held in bits [1, 9) of a 16-bit-counter address (OPT_FOLD)
+template <bool DH_FMA = false>
 __device__ __forceinline__ void match_entry_ballot_fma(uint32_t e, uint32_t ones, uint32_t& b, uint32_t& c)
 {
+  uint32_t dh;
+  if (DH_FMA)
+  {
+    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(dh) : "r"(e), "r"(ones & 0x08000000u)); // e >> 5 on the FMA pipe
+  }
+  else
+  {
+    dh = e >> 5;
+  }
   asm volatile(
     "{\n"
     ".reg .pred p0, p1, p2, p3;\n"
-    ".reg .b32 v0, v1, v2, v3, v4, v5, v6, v7, t, dh;\n"
-    "shr.u32 dh, %2, 5;\n"
+    ".reg .b32 v0, v1, v2, v3, v4, v5, v6, v7, t;\n"
     "and.b32 t, %2, 2; setp.ne.u32 p0, t, 0;\n"
     "and.b32 t, %2, 4; setp.ne.u32 p1, t, 0;\n"
     "and.b32 t, %2, 8; setp.ne.u32 p2, t, 0;\n"
@@ -458,10 +469,10 @@ __device__ __forceinline__ void match_entry_ballot_fma(uint32_t e, uint32_t ones
     "@!p1 mad.lo.u32 v1, v1, %3, %3;\n"
     "@!p2 mad.lo.u32 v2, v2, %3, %3;\n"
     "@!p3 mad.lo.u32 v3, v3, %3, %3;\n"
-    "and.b32 t, dh, 1; setp.ne.u32 p0, t, 0;\n"
-    "and.b32 t, dh, 2; setp.ne.u32 p1, t, 0;\n"
-    "and.b32 t, dh, 4; setp.ne.u32 p2, t, 0;\n"
-    "and.b32 t, dh, 8; setp.ne.u32 p3, t, 0;\n"
+    "and.b32 t, %4, 1; setp.ne.u32 p0, t, 0;\n"
+    "and.b32 t, %4, 2; setp.ne.u32 p1, t, 0;\n"
+    "and.b32 t, %4, 4; setp.ne.u32 p2, t, 0;\n"
+    "and.b32 t, %4, 8; setp.ne.u32 p3, t, 0;\n"
     "vote.sync.ballot.b32 v4, p0, 0xffffffff;\n"
     "vote.sync.ballot.b32 v5, p1, 0xffffffff;\n"
     "vote.sync.ballot.b32 v6, p2, 0xffffffff;\n"
@@ -475,7 +486,7 @@ __device__ __forceinline__ void match_entry_ballot_fma(uint32_t e, uint32_t ones
     "lop3.b32 %1, v6, v7, t, 0x80;\n"
     "}\n"
     : "=r"(b), "=r"(c)
-    : "r"(e), "r"(ones));
+    : "r"(e), "r"(ones), "r"(dh));
 }
 
 // Decoupled look-back of one digit over the predecessor tiles (status words `base[t * RADIX]`, t < tile), W words per
@@ -675,7 +686,7 @@ __device__ __forceinline__ void onesweep_tile(
     if (FOLD)
     {
       ctr = digit_entry<FLOATK>(uint32_t(key[i]), rot_ctr, msk_ctr, s_mine, uint32_t(neg_zero), uint32_t(pos_zero));
-      match_entry_ballot_fma(ctr, a.all_ones, b, c);
+      match_entry_ballot_fma<(OPT & OPT_DH_FMA) != 0>(ctr, a.all_ones, b, c);
     }
     else
     {

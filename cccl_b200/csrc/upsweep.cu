@@ -10,9 +10,14 @@ static cudaError_t launch_hist_p(
   const void* keys, unsigned long long n, unsigned long long* bins, int begin_bit, int end_bit, const KeyXform& xf,
   unsigned grid, cudaStream_t stream, uint32_t* zero_flag)
 {
-  using L     = HistLayout<int(sizeof(U))>;
-  auto kernel = histogram_kernel<U, PASSES>;
-  const size_t smem = size_t(PASSES) * RADIX * L::REPLICAS * 4;
+  using L = HistLayout<int(sizeof(U))>;
+  // identity / integer / floating-point transform (histogram.cuh); 8-byte keys have one body
+  const int mode = xf.float_mask != 0 ? 2 : ((xf.sign_mask != 0 || xf.desc_mask != 0) ? 1 : 0);
+  auto kernel    = sizeof(U) > 4 || mode == 2 ? histogram_kernel<U, PASSES, 2>
+                 : mode == 1                  ? histogram_kernel<U, PASSES, 1>
+                                              : histogram_kernel<U, PASSES, 0>;
+  // keys of at most 32 bits: one table more, the kernel aligns its counters to the size of one pass's table (histogram.cuh)
+  const size_t smem = size_t(PASSES + (sizeof(U) <= 4 && PASSES <= 4 ? 1 : 0)) * RADIX * L::REPLICAS * 4;
   if (smem > 48 * 1024)
   {
     // per-device attribute; cheap and idempotent, legal during stream capture

@@ -285,7 +285,7 @@ def test_every_compiled_config_is_correct():
         lib.b200rs_set_config(-1)
 
 
-@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64, np.float32])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.int16, np.float16, np.uint32, np.int32, np.uint64, np.float32])
 def test_upsweep_histogram_alone(dtype):
     for n, off in ((0, 0), (5, 1), (100_003, 0), (100_003, 3), (1 << 20, 1)):
         k = make_keys("entropy2", n, dtype, seed=3)
@@ -297,6 +297,12 @@ def test_upsweep_histogram_alone(dtype):
     bits = np.dtype(dtype).itemsize * 8
     got = gpu_histogram(k, begin_bit=bits // 3, end_bit=bits - 1)
     assert np.array_equal(got, oracle_histogram(k, begin_bit=bits // 3, end_bit=bits - 1))
+    # every window start modulo 8 and narrow last digits (the folded addressing rotates by begin_bit - 7 modulo 32)
+    for b in range(0, min(bits, 12)):
+        for e in sorted({b + 1, min(bits, b + 9), bits}):
+            for desc in (False, True):
+                got = gpu_histogram(k, descending=desc, begin_bit=b, end_bit=e)
+                assert np.array_equal(got, oracle_histogram(k, descending=desc, begin_bit=b, end_bit=e)), (dtype, b, e, desc)
 
 
 def test_cuda_graph_capture(sort_path):

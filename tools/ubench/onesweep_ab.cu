@@ -183,10 +183,10 @@ int main(int argc, char** argv)
   CK(cudaMemset(c.bins, 0, 4 * RADIX * 8));
   {
     using L     = HistLayout<4>;
-    auto kernel = histogram_kernel<uint32_t, 4>;
-    const size_t smem = size_t(4) * RADIX * L::REPLICAS * 4;
+    auto kernel = histogram_kernel<uint32_t, 4, 0>;
+    const size_t smem = size_t(4 + 1) * RADIX * L::REPLICAS * 4; // + the alignment slack of the folded addressing
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kernel<<<c.sms, HIST_THREADS, smem>>>(c.keys, c.n, c.bins, 0, 32, make_xform(0, 4, 0));
+    kernel<<<c.sms, HIST_THREADS, smem>>>(c.keys, c.n, c.bins, 0, 32, make_xform(0, 4, 0), nullptr);
     scan_bins_kernel<<<4, RADIX>>>(c.bins);
   }
   CK(cudaDeviceSynchronize());
