@@ -78,6 +78,42 @@ def _describe(arr):
     return cai["data"][0], np.dtype(cai["typestr"]), n
 
 
+def _device_index(arr):
+    """CUDA device ordinal an array lives on, or None when it cannot be told (plain __cuda_array_interface__ objects)."""
+    if arr is None:
+        return None
+    if hasattr(arr, "is_cuda") and hasattr(arr, "device"):
+        return arr.device.index
+    dev = getattr(arr, "device", None)  # cupy: arr.device.id
+    return getattr(dev, "id", None)
+
+
+class _on_device_of:
+    """The C library launches on the CURRENT device and stream (cudaGetDevice, as the reference does,
+    dispatch_radix_sort.cuh:1764-1772): make the device of the arrays current for the call, take that device's current
+    stream when none was given, and refuse arrays that live on different devices."""
+
+    def __init__(self, *arrays):
+        found = {d for d in (_device_index(a) for a in arrays) if d is not None}
+        if len(found) > 1:
+            raise ValueError(f"keys, values and temporary storage must be on one device, got devices {sorted(found)}")
+        self.index = found.pop() if found else None
+        self.guard = None
+
+    def __enter__(self):
+        if self.index is not None:
+            import torch
+
+            self.guard = torch.cuda.device(self.index)
+            self.guard.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
+
+
 def key_kind_of(dtype: np.dtype) -> int:
     if dtype.kind == "f":
         return _native.KEY_FLOAT
@@ -147,9 +183,10 @@ class _RadixSort:
             d_temp, _, _ = _describe(temp_storage)
             temp_bytes = temp_storage.numel() * temp_storage.element_size() if hasattr(temp_storage, "numel") \
                 else temp_storage.nbytes
-        temp_bytes, selector = _native.sort_raw(
-            d_temp, temp_bytes, pk_in, pk_out, pv_in, pv_out, num_items, self.key_kind, kdt.itemsize, vbytes,
-            begin_bit, end_bit, self.order is SortOrder.DESCENDING, is_overwrite_okay, _stream_handle(stream))
+        with _on_device_of(kin, kout, vin, vout, temp_storage):
+            temp_bytes, selector = _native.sort_raw(
+                d_temp, temp_bytes, pk_in, pk_out, pv_in, pv_out, num_items, self.key_kind, kdt.itemsize, vbytes,
+                begin_bit, end_bit, self.order is SortOrder.DESCENDING, is_overwrite_okay, _stream_handle(stream))
         if is_overwrite_okay and temp_storage is not None:
             assert selector in (0, 1)
             # the C ABI numbers buffers as (in=0, out=1) == (current, alternate) at call time

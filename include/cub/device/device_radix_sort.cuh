@@ -198,6 +198,13 @@ inline cudaError_t b200rs_fields_sort_db(
 template <class ValueT>
 constexpr int b200rs_value_bytes_of()
 {
+  // the library moves values as opaque blobs of these sizes; 16-byte values must be 8-byte aligned (they are loaded
+  // and stored as two 64-bit words).  Anything else would be a cudaErrorNotSupported / misaligned access at run time.
+  static_assert(std::is_same<std::remove_cv_t<ValueT>, NullType>::value || sizeof(ValueT) == 1 || sizeof(ValueT) == 2
+                  || sizeof(ValueT) == 4 || sizeof(ValueT) == 8 || sizeof(ValueT) == 16,
+                "value types of 1, 2, 4, 8 or 16 bytes (wrap other sizes in an index sort + gather)");
+  static_assert(std::is_same<std::remove_cv_t<ValueT>, NullType>::value || sizeof(ValueT) != 16 || alignof(ValueT) >= 8,
+                "16-byte value types must be at least 8-byte aligned");
   return std::is_same<std::remove_cv_t<ValueT>, NullType>::value ? 0 : int(sizeof(ValueT));
 }
 

@@ -8,7 +8,8 @@
 // Every call is ONE b200rs_sort_inplace (include/b200rs.h): scratch from the stream-ordered pool, DoubleBuffer sort,
 // copy-back iff needed, synchronise (the reference synchronises unless the policy is par_nosync,
 // sort.h:260 `synchronize_optional`).  A non-zero return throws thrust::system_error like the reference
-// (sort.h:260-262).  No other backend exists here: host iterators or non-arithmetic keys are compile errors.
+// (sort.h:260-262).  Comparators other than less / greater take cub::DeviceMergeSort (include/cub/device/
+// device_merge_sort.cuh), as the reference's __smart_sort does.  No host backend exists here.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -25,6 +26,9 @@
 
 #include "../b200rs.h"
 #include "device_vector.h"
+#ifdef __CUDACC__
+#  include "../cub/device/device_merge_sort.cuh"
+#endif
 
 namespace thrust
 {
@@ -136,6 +140,79 @@ void radix_sort_pairs(const cuda::execute_on_stream& pol, KeyIt first, KeyIt las
                                      reinterpret_cast<b200rs_stream_t>(pol.stream));
   throw_on_error(static_cast<cudaError_t>(rc), "radix_sort: failed on 2nd step");
 }
+
+// Any other comparator (a user functor, a lambda, less / greater on a key type without a bit-ordered image) takes the
+// comparison sort, as in the reference (sort.h:288-301 -> __merge_sort): cub::DeviceMergeSort of this repo, whose
+// kernels are templates instantiated here by the caller's nvcc (a comparator cannot cross the C ABI).
+#ifdef __CUDACC__
+template <class K, class V, class Compare>
+void merge_sort_impl(const cuda::execute_on_stream& pol, K* k, V* v, unsigned long long n, Compare comp)
+{
+  size_t bytes = 0;
+  auto call    = [&](void* t) {
+    if constexpr (std::is_same<V, ::cub::NullType>::value)
+    {
+      return ::cub::DeviceMergeSort::StableSortKeys(t, bytes, k, n, comp, pol.stream);
+    }
+    else
+    {
+      return ::cub::DeviceMergeSort::StableSortPairs(t, bytes, k, v, n, comp, pol.stream);
+    }
+  };
+  throw_on_error(call(nullptr), "merge_sort: failed on 1st step");
+  void* temp = nullptr;
+  throw_on_error(cudaMallocAsync(&temp, bytes, pol.stream), "merge_sort: failed to get memory buffer");
+  const cudaError_t e = call(temp);
+  const cudaError_t f = cudaFreeAsync(temp, pol.stream);
+  throw_on_error(e, "merge_sort: failed on 2nd step");
+  throw_on_error(f, "merge_sort: failed to free memory buffer");
+  if (pol.sync)
+  {
+    throw_on_error(cudaStreamSynchronize(pol.stream), "merge_sort: failed to synchronize");
+  }
+}
+#endif
+
+template <class KeyIt, class Compare>
+void sort_keys(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Compare comp)
+{
+  using K = std::remove_pointer_t<decltype(unwrap(first))>;
+  if constexpr (radix_order<Compare>::value != 0 && std::is_arithmetic<K>::value)
+  {
+    radix_sort_keys(pol, first, last, comp);
+  }
+  else
+  {
+#ifdef __CUDACC__
+    static_assert(radix_order<Compare>::value == 0 || std::is_void<K>::value,
+                  "less<T> / greater<T> of a non-arithmetic key type: pass a comparator with operator()");
+    merge_sort_impl(pol, unwrap(first), static_cast<::cub::NullType*>(nullptr),
+                    static_cast<unsigned long long>(unwrap(last) - unwrap(first)), comp);
+#else
+    static_assert(radix_order<Compare>::value != 0, "user comparators need nvcc (the merge-sort kernels are templates)");
+#endif
+  }
+}
+template <class KeyIt, class ValIt, class Compare>
+void sort_pairs(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values, Compare comp)
+{
+  using K = std::remove_pointer_t<decltype(unwrap(first))>;
+  if constexpr (radix_order<Compare>::value != 0 && std::is_arithmetic<K>::value)
+  {
+    radix_sort_pairs(pol, first, last, values, comp);
+  }
+  else
+  {
+#ifdef __CUDACC__
+    static_assert(radix_order<Compare>::value == 0 || std::is_void<K>::value,
+                  "less<T> / greater<T> of a non-arithmetic key type: pass a comparator with operator()");
+    merge_sort_impl(pol, unwrap(first), unwrap(values), static_cast<unsigned long long>(unwrap(last) - unwrap(first)),
+                    comp);
+#else
+    static_assert(radix_order<Compare>::value != 0, "user comparators need nvcc (the merge-sort kernels are templates)");
+#endif
+  }
+}
 } // namespace detail
 
 // ---- sort / stable_sort (radix sort is stable, so both names are the same call, as in the reference)
@@ -144,40 +221,40 @@ void sort(KeyIt first, KeyIt last)
 {
   detail::radix_sort_keys(device, first, last, less<>{});
 }
-template <class KeyIt, class T, template <class> class Cmp>
-void sort(KeyIt first, KeyIt last, Cmp<T> comp)
+template <class KeyIt, class Compare>
+void sort(KeyIt first, KeyIt last, Compare comp)
 {
-  detail::radix_sort_keys(device, first, last, comp);
+  detail::sort_keys(device, first, last, comp);
 }
 template <class KeyIt>
 void sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last)
 {
   detail::radix_sort_keys(pol, first, last, less<>{});
 }
-template <class KeyIt, class T, template <class> class Cmp>
-void sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Cmp<T> comp)
+template <class KeyIt, class Compare>
+void sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Compare comp)
 {
-  detail::radix_sort_keys(pol, first, last, comp);
+  detail::sort_keys(pol, first, last, comp);
 }
 template <class KeyIt>
 void stable_sort(KeyIt first, KeyIt last)
 {
   detail::radix_sort_keys(device, first, last, less<>{});
 }
-template <class KeyIt, class T, template <class> class Cmp>
-void stable_sort(KeyIt first, KeyIt last, Cmp<T> comp)
+template <class KeyIt, class Compare>
+void stable_sort(KeyIt first, KeyIt last, Compare comp)
 {
-  detail::radix_sort_keys(device, first, last, comp);
+  detail::sort_keys(device, first, last, comp);
 }
 template <class KeyIt>
 void stable_sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last)
 {
   detail::radix_sort_keys(pol, first, last, less<>{});
 }
-template <class KeyIt, class T, template <class> class Cmp>
-void stable_sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Cmp<T> comp)
+template <class KeyIt, class Compare>
+void stable_sort(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, Compare comp)
 {
-  detail::radix_sort_keys(pol, first, last, comp);
+  detail::sort_keys(pol, first, last, comp);
 }
 
 // ---- sort_by_key / stable_sort_by_key
@@ -186,40 +263,40 @@ void sort_by_key(KeyIt first, KeyIt last, ValIt values)
 {
   detail::radix_sort_pairs(device, first, last, values, less<>{});
 }
-template <class KeyIt, class ValIt, class T, template <class> class Cmp>
-void sort_by_key(KeyIt first, KeyIt last, ValIt values, Cmp<T> comp)
+template <class KeyIt, class ValIt, class Compare>
+void sort_by_key(KeyIt first, KeyIt last, ValIt values, Compare comp)
 {
-  detail::radix_sort_pairs(device, first, last, values, comp);
+  detail::sort_pairs(device, first, last, values, comp);
 }
 template <class KeyIt, class ValIt>
 void sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values)
 {
   detail::radix_sort_pairs(pol, first, last, values, less<>{});
 }
-template <class KeyIt, class ValIt, class T, template <class> class Cmp>
-void sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values, Cmp<T> comp)
+template <class KeyIt, class ValIt, class Compare>
+void sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values, Compare comp)
 {
-  detail::radix_sort_pairs(pol, first, last, values, comp);
+  detail::sort_pairs(pol, first, last, values, comp);
 }
 template <class KeyIt, class ValIt>
 void stable_sort_by_key(KeyIt first, KeyIt last, ValIt values)
 {
   detail::radix_sort_pairs(device, first, last, values, less<>{});
 }
-template <class KeyIt, class ValIt, class T, template <class> class Cmp>
-void stable_sort_by_key(KeyIt first, KeyIt last, ValIt values, Cmp<T> comp)
+template <class KeyIt, class ValIt, class Compare>
+void stable_sort_by_key(KeyIt first, KeyIt last, ValIt values, Compare comp)
 {
-  detail::radix_sort_pairs(device, first, last, values, comp);
+  detail::sort_pairs(device, first, last, values, comp);
 }
 template <class KeyIt, class ValIt>
 void stable_sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values)
 {
   detail::radix_sort_pairs(pol, first, last, values, less<>{});
 }
-template <class KeyIt, class ValIt, class T, template <class> class Cmp>
-void stable_sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values, Cmp<T> comp)
+template <class KeyIt, class ValIt, class Compare>
+void stable_sort_by_key(const cuda::execute_on_stream& pol, KeyIt first, KeyIt last, ValIt values, Compare comp)
 {
-  detail::radix_sort_pairs(pol, first, last, values, comp);
+  detail::sort_pairs(pol, first, last, values, comp);
 }
 
 } // namespace thrust

@@ -41,24 +41,33 @@ def test_shim_programs_link_against_the_product_library():
         assert "libb200rs.so" in out
 
 
-def test_thrust_shim_rejects_non_radix_comparators(tmp_path):
-    """A comparator that is not less/greater (thrust, std, cuda::std) must not compile: the reference would run its
-    merge sort (thrust/system/cuda/detail/sort.h:288-339), this path has none and must not sort ascending silently."""
+def test_thrust_shim_comparator_routing(tmp_path):
+    """less / greater (thrust, std, cuda::std) on arithmetic keys select the radix path; any other comparator compiles
+    into the comparison sort (cub::DeviceMergeSort of this repo), as the reference's __smart_sort does
+    (thrust/system/cuda/detail/sort.h:288-339) -- never a silent ascending radix sort; less<T> on a key type without
+    operator< support in the shim is a compile error with a message."""
     nvcc = "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     body = """#include <thrust/sort.h>
-template <class T> struct by_abs { bool operator()(T a, T b) const { return (a < 0 ? -a : a) < (b < 0 ? -b : b); } };
-int main() { int* d = nullptr; thrust::sort(d, d, %s); return 0; }
+template <class T> struct by_abs { __host__ __device__ bool operator()(T a, T b) const { return (a < 0 ? -a : a) < (b < 0 ? -b : b); } };
+struct item { int a; float b; };
+int main() { %s* d = nullptr; thrust::sort(d, d, %s); return 0; }
 """
-    for comp, ok in (("thrust::greater<int>()", True), ("std::greater<int>()", True), ("by_abs<int>()", False)):
+    for ktype, comp, ok, symbol in (("int", "thrust::greater<int>()", True, None), ("int", "std::greater<int>()", True, None),
+                                    ("int", "by_abs<int>()", True, "merge_pass_kernel"),
+                                    ("item", "thrust::less<item>()", False, None)):
         src = tmp_path / "t.cu"
-        src.write_text(body % comp)
+        src.write_text(body % (ktype, comp))
+        obj = tmp_path / "t.o"
         res = subprocess.run([nvcc, "-std=c++17", "-arch=sm_100a", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
-                              str(tmp_path / "t.o")], capture_output=True, text=True, timeout=300)
+                              str(obj)], capture_output=True, text=True, timeout=300)
         assert (res.returncode == 0) == ok, (comp, res.stderr[-1500:])
         if not ok:
-            assert "merge sort" in res.stderr
+            assert "non-arithmetic key type" in res.stderr
+        else:
+            syms = subprocess.run(["cuobjdump", "-elf", str(obj)], capture_output=True, text=True).stdout
+            assert ("merge_pass_kernel" in syms) == (symbol is not None), comp
 
 
 @pytest.mark.gpu

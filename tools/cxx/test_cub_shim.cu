@@ -7,6 +7,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_radix_sort.cuh>
 #include <cub/device/device_topk.cuh>
+#include <cub/device/device_merge_sort.cuh>
 
 #include <cuda/stream_ref>
 
@@ -935,6 +936,96 @@ void topk_cases(cudaStream_t stream, size_t max_n)
   REQUIRE(cub::DeviceTopK::MinKeys(ki.p, ko.p, 0, 3) == cudaSuccess);
 }
 
+// cub::DeviceMergeSort (device_merge_sort.cuh:250,467,712,926,1126,1313,1502): arbitrary comparators and key types, every
+// variant stable; checked against std::stable_sort with the same comparator (as catch2_test_device_merge_sort.cu does).
+struct ms_item
+{
+  int group;
+  float weight;
+  unsigned short tag;
+};
+struct ms_item_less
+{
+  __host__ __device__ bool operator()(const ms_item& a, const ms_item& b) const
+  {
+    return a.group != b.group ? a.group < b.group : a.weight > b.weight;
+  }
+};
+struct ms_mod_less
+{
+  unsigned m;
+  __host__ __device__ bool operator()(unsigned a, unsigned b) const
+  {
+    return a % m < b % m;
+  }
+};
+
+void merge_sort_case(size_t n, unsigned mod, cudaStream_t stream)
+{
+  std::mt19937 rng(unsigned(n * 13 + mod));
+  std::vector<unsigned> keys(n);
+  std::vector<unsigned long long> vals(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    keys[i] = rng();
+    vals[i] = i;
+  }
+  const ms_mod_less cmp{mod};
+  // expected: stable sort of the indices
+  std::vector<unsigned long long> perm(vals);
+  std::stable_sort(perm.begin(), perm.end(), [&](unsigned long long a, unsigned long long b) { return cmp(keys[a], keys[b]); });
+  std::vector<unsigned> want(n);
+  for (size_t i = 0; i < n; ++i)
+  {
+    want[i] = keys[perm[i]];
+  }
+  { // in place, pairs
+    dev<unsigned> k(keys);
+    dev<unsigned long long> v(vals);
+    size_t bytes = 0;
+    REQUIRE(cub::DeviceMergeSort::SortPairs(nullptr, bytes, k.p, v.p, n, cmp, stream) == cudaSuccess);
+    dev<unsigned char> temp(bytes);
+    REQUIRE(cub::DeviceMergeSort::SortPairs(temp.p, bytes, k.p, v.p, n, cmp, stream) == cudaSuccess);
+    REQUIRE(cudaStreamSynchronize(stream) == cudaSuccess);
+    REQUIRE(k.host() == want);
+    REQUIRE(v.host() == perm);
+  }
+  { // copy, keys only: the input stays untouched
+    dev<unsigned> k(keys), o(n);
+    size_t bytes = 0;
+    REQUIRE(cub::DeviceMergeSort::StableSortKeysCopy(nullptr, bytes, k.p, o.p, n, cmp, stream) == cudaSuccess);
+    dev<unsigned char> temp(bytes);
+    REQUIRE(cub::DeviceMergeSort::StableSortKeysCopy(temp.p, bytes, k.p, o.p, n, cmp, stream) == cudaSuccess);
+    REQUIRE(cudaStreamSynchronize(stream) == cudaSuccess);
+    REQUIRE(o.host() == want);
+    REQUIRE(k.host() == keys);
+  }
+  { // struct keys with 1-byte values, env overload owning its temporary storage
+    std::vector<ms_item> items(n);
+    std::vector<unsigned char> tags(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+      items[i] = ms_item{int(rng() % 7), float(rng() % 5), (unsigned short) i};
+      tags[i]  = (unsigned char) (i * 7);
+    }
+    std::vector<size_t> p2(n);
+    std::iota(p2.begin(), p2.end(), size_t(0));
+    std::stable_sort(p2.begin(), p2.end(), [&](size_t a, size_t b) { return ms_item_less{}(items[a], items[b]); });
+    dev<ms_item> k(items);
+    dev<unsigned char> v(tags);
+    REQUIRE(cub::DeviceMergeSort::StableSortPairs(k.p, v.p, n, ms_item_less{}, cuda::stream_ref{stream}) == cudaSuccess);
+    REQUIRE(cudaStreamSynchronize(stream) == cudaSuccess);
+    auto gk = k.host();
+    auto gv = v.host();
+    bool ok = true;
+    for (size_t i = 0; i < n; ++i)
+    {
+      ok = ok && gk[i].tag == items[p2[i]].tag && gk[i].group == items[p2[i]].group && gv[i] == tags[p2[i]];
+    }
+    REQUIRE(ok);
+  }
+}
+
 int main()
 {
   cudaStream_t stream;
@@ -950,6 +1041,15 @@ int main()
   env_api_goldens();
   edge_cases();
   topk_cases(stream, max_n);
+  for (size_t n : {size_t(0), size_t(1), size_t(2), size_t(255), size_t(2047), size_t(2048), size_t(2049), size_t(6145),
+                   size_t(100003), size_t((1u << 21) + 77)})
+  {
+    if (n <= max_n)
+    {
+      merge_sort_case(n, 1000, stream); // many ties: stability visible
+      merge_sort_case(n, 0x7fffffffu, stream);
+    }
+  }
   for (size_t n : {size_t(3000), size_t(77777)})
   {
     partition_case(n, 1);

@@ -26,6 +26,14 @@ static int g_failed = 0;
     }                                                                     \
   } while (0)
 
+struct by_last_digit
+{
+  __host__ __device__ bool operator()(int a, int b) const
+  {
+    return a % 10 < b % 10;
+  }
+};
+
 template <class K>
 void random_case(size_t n, bool desc)
 {
@@ -95,6 +103,26 @@ int main()
     ASSERT_TRUE((v.to_host() == std::vector<int>{0, 1, 2, 3, 4, 5, 6}));
     thrust::stable_sort(v.begin(), v.end(), ::cuda::std::greater<int>());
     ASSERT_TRUE((v.to_host() == std::vector<int>{6, 5, 4, 3, 2, 1, 0}));
+  }
+  { // user comparators take the comparison sort (sort.h:288-301 -> merge sort), stable
+    std::vector<int> h(50001);
+    std::mt19937 rng(7);
+    for (auto& x : h)
+    {
+      x = int(rng() % 100000);
+    }
+    std::vector<int> idx(h.size());
+    std::iota(idx.begin(), idx.end(), 0);
+    thrust::device_vector<int> k(h), v(idx);
+    thrust::sort_by_key(k.begin(), k.end(), v.begin(), by_last_digit());
+    std::vector<int> p(idx);
+    std::stable_sort(p.begin(), p.end(), [&](int a, int b) { return h[a] % 10 < h[b] % 10; });
+    ASSERT_TRUE(v.to_host() == p);
+    thrust::device_vector<int> k2(h);
+    thrust::stable_sort(k2.begin(), k2.end(), by_last_digit());
+    std::vector<int> e(h);
+    std::stable_sort(e.begin(), e.end(), [](int a, int b) { return a % 10 < b % 10; });
+    ASSERT_TRUE(k2.to_host() == e);
   }
   { // TestSortByKeySimple (thrust/testing/sort_by_key.cu:46-53)
     thrust::device_vector<int> k(std::vector<int>{1, 3, 6, 5, 2, 0, 4});
