@@ -451,24 +451,25 @@ def run_single_gpu(args):
                         d_out_values=sl["vals_out"].view(torch.int32) if vals is not None else None,
                         num_items=n, begin_bit=b, end_bit=e)
 
-    def e2e_step(i, depth):
+    def e2e_step(i, depth, do_sort=True):
         sl = slots[i % depth]
         with torch.cuda.stream(sl["stream"]):
             sl["keys"].copy_(h_in, non_blocking=True)
             if vals is not None:
                 sl["vals"].copy_(h_vin, non_blocking=True)
-            sorter(temp_storage=sl["temp"], stream=sl["stream"], **sl["kw"])
+            if do_sort:
+                sorter(temp_storage=sl["temp"], stream=sl["stream"], **sl["kw"])
             sl["h_out"].copy_(sl["keys_out"], non_blocking=True)
             if vals is not None:
                 sl["h_vout"].copy_(sl["vals_out"], non_blocking=True)
 
-    def e2e_run(depth):
-        e2e_step(0, depth)
+    def e2e_run(depth, do_sort=True):
+        e2e_step(0, depth, do_sort)
         torch.cuda.synchronize()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record(slots[0]["stream"])  # every stream is idle here: this is the start of the first H2D
         for i in range(e2e_steps):
-            e2e_step(i, depth)
+            e2e_step(i, depth, do_sort)
         cur = torch.cuda.current_stream()
         for sl in slots[:depth]:
             cur.wait_stream(sl["stream"])
@@ -478,11 +479,15 @@ def run_single_gpu(args):
 
     e2e_steps = max(3, min(args.steps, 12))
     e2e_serial_ms = e2e_run(1)
+    # the host-link ceiling: the same pinned-host H2D + D2H of every step with NO sort in between (not part of `value`)
+    e2e_copies_ms = e2e_run(DEPTH, do_sort=False)
     e2e_ms = e2e_run(DEPTH)
     e2e = {"value": n / (e2e_ms * 1e-3) / 1e9, "unit": "Gkeys/s", "h2d_bytes_per_step": n * (kb + vb),
            "d2h_bytes_per_step": n * (kb + vb), "ms_per_step": e2e_ms, "steps": e2e_steps,
            "steps_in_flight": DEPTH, "timer": "CUDA events: first H2D start -> join of all streams",
-           "serial_value": n / (e2e_serial_ms * 1e-3) / 1e9, "serial_ms_per_step": e2e_serial_ms}
+           "serial_value": n / (e2e_serial_ms * 1e-3) / 1e9, "serial_ms_per_step": e2e_serial_ms,
+           "copies_only_ms_per_step": e2e_copies_ms,
+           "note": "copies_only = the same H2D + D2H per step, same streams, without the sort: the host-link ceiling"}
 
     # spot check the last e2e result on the host (sortedness of a sample); full parity lives in tests/
     if kdt == "uint32" and b == 0 and e == 32 and not desc:
@@ -507,6 +512,21 @@ def run_single_gpu(args):
                 extra.append(device_leg(w, max(3, min(args.steps, 10)), 3, with_cub=not args.no_cub))
             except Exception as ex:  # reported, never fatal for the headline line
                 extra.append({"workload": w, "error": str(ex)[:200]})
+        # the adjacent caller of SURVEY 8f-4: top-k selection (b200rs_topk vs the unmodified cub::DeviceTopK on this GPU)
+        try:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+            import topk_bench
+
+            for log2k, rounds in ((11, 1), (11, 5), (23, 1)):
+                o = topk_bench.ours(28, log2k, rounds, iters=10)
+                c = None if args.no_cub else topk_bench.cub(28, log2k, rounds, iters=5)
+                extra.append({"workload": f"topk_u32_2^28_k2^{log2k}_" + ("uniform" if rounds == 1 else "entropy0.201"),
+                              "value": o["gkeys_per_s"], "unit": "Gkeys/s", "ms_per_step": o["ms"],
+                              "algorithmic_bytes": (1 << 28) * 4 + (1 << log2k) * 4,
+                              "frac_of_one_read": ((1 << 28) * 4 / (o["ms"] * 1e-3) / 1e9) / measured_peaks()[0],
+                              "cub_same_gpu": c.get("gkeys_per_s") if c else None})
+        except Exception as ex:
+            extra.append({"workload": "topk_u32_2^28", "error": str(ex)[:200]})
 
     line = {
         "metric": METRIC,
