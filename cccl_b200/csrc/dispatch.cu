@@ -717,6 +717,32 @@ int b200rs_sort(
 
 } // extern "C"
 
+// Host-built tables of the partition pass travel as KERNEL ARGUMENTS (copied by value at launch, so the call stays legal
+// under stream capture and never reads pageable host memory asynchronously).
+struct PartitionTables
+{
+  PeerTable peer;
+  unsigned long long bucket_offsets[31];
+  uint32_t num_buckets;
+  uint32_t write_peer;
+};
+__global__ void write_partition_tables_kernel(const PartitionTables t, PeerTable* peer_out, unsigned long long* bins_out)
+{
+  if (t.write_peer != 0)
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&t.peer);
+    uint32_t* dst       = reinterpret_cast<uint32_t*>(peer_out);
+    for (uint32_t w = threadIdx.x; w < uint32_t(sizeof(PeerTable) / 4); w += blockDim.x)
+    {
+      dst[w] = src[w];
+    }
+  }
+  if (threadIdx.x < t.num_buckets)
+  {
+    bins_out[threadIdx.x] = t.bucket_offsets[threadIdx.x];
+  }
+}
+
 // The partition pass (one onesweep launch in bucket mode).  num_dests == 0: results go to d_keys_out / d_values_out;
 // otherwise the partitioned order is cut at h_segment_ends and segment r is stored through the (biased) pointers
 // h_rank_dst_keys[r] / h_rank_dst_vals[r] -- peer-mapped receive buffers of the destination GPUs.
@@ -819,11 +845,13 @@ static int partition_impl(
   {
     return int(e);
   }
+  PartitionTables tables;
+  memset(&tables, 0, sizeof(tables));
   if (remote && d_plan == nullptr)
   {
     // which rank each bucket goes to (0 = a segment boundary falls inside it: resolved per item in the kernel)
-    PeerTable pt;
-    memset(&pt, 0, sizeof(pt));
+    PeerTable& pt = tables.peer;
+    tables.write_peer = 1;
     pt.num_dests = uint32_t(num_dests);
     for (int r = 0; r < num_dests; ++r)
     {
@@ -846,17 +874,18 @@ static int partition_impl(
       pt.bucket_dst_keys[b]   = one_rank ? pt.rank_dst_keys[r_lo] : 0;
       pt.bucket_dst_vals[b]   = one_rank ? pt.rank_dst_vals[r_lo] : 0;
     }
-    e = cudaMemcpyAsync(base + off_peer, &pt, sizeof(pt), cudaMemcpyHostToDevice, stream);
-    if (e != cudaSuccess)
-    {
-      return int(e);
-    }
   }
   // exclusive bucket offsets (2 * num_splitters + 1 of them) -> the pass's per-digit output offsets
   if (d_plan == nullptr)
   {
-    e = cudaMemcpyAsync(base + off_bins, h_bucket_offsets, size_t(2 * num_splitters + 1) * sizeof(uint64_t),
-                        cudaMemcpyHostToDevice, stream);
+    tables.num_buckets = uint32_t(2 * num_splitters + 1);
+    for (uint32_t b = 0; b < tables.num_buckets; ++b)
+    {
+      tables.bucket_offsets[b] = h_bucket_offsets[b];
+    }
+    write_partition_tables_kernel<<<1, 256, 0, stream>>>(
+      tables, reinterpret_cast<PeerTable*>(base + off_peer), reinterpret_cast<unsigned long long*>(base + off_bins));
+    e = cudaPeekAtLastError();
     if (e != cudaSuccess)
     {
       return int(e);
