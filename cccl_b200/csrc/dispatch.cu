@@ -12,7 +12,10 @@
 #include "../../include/b200rs.h"
 #include "configs.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <atomic>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -50,8 +53,39 @@ enum OpKind
   OP_SMALL     = 6
 };
 
+// B200RS_DEBUG_SYNC=1 in the environment (the counterpart of the reference's CUB_DEBUG_SYNC / CubDebug logging,
+// /root/reference/cub/cub/util_debug.cuh:37-72): every stream operation of b200rs_sort is followed by a stream
+// synchronisation and its status is logged to stderr.  Ignored while the stream is being captured.
+static int debug_sync_level()
+{
+  static const int level = [] {
+    const char* v = getenv("B200RS_DEBUG_SYNC");
+    return v != nullptr ? atoi(v) : 0;
+  }();
+  return level;
+}
+static thread_local int t_prev_kind = -1;
+static void debug_sync(cudaStream_t stream)
+{
+  if (debug_sync_level() <= 0 || t_prev_kind < 0)
+  {
+    return;
+  }
+  static const char* const names[] = {"memset", "histogram", "scan", "onesweep", "copy", "single_tile", "small_sort"};
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+  {
+    const cudaError_t e = cudaStreamSynchronize(stream);
+    fprintf(stderr, "b200rs_sort: op %d (%s) on stream %p: %s\n", t_last_launches, names[t_prev_kind], (void*) stream,
+            cudaGetErrorString(e));
+  }
+  t_prev_kind = -1;
+}
+
 static void mark_op(cudaStream_t stream, int kind)
 {
+  debug_sync(stream);
+  t_prev_kind = kind;
   t_last_launches++;
   if (!t_timing_on || t_events_used >= MAX_TIMED_OPS)
   {
@@ -72,6 +106,7 @@ static void mark_op(cudaStream_t stream, int kind)
 
 static void mark_end(cudaStream_t stream)
 {
+  debug_sync(stream);
   if (t_timing_on && t_events_used > 0 && t_events_used < t_events_made)
   {
     cudaEventRecord(t_events[t_events_used], stream);
@@ -400,6 +435,28 @@ int b200rs_sort(
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   t_last_launches     = 0;
   t_events_used       = 0;
+  t_prev_kind         = -1;
+  // an NVTX range around the execute call only, as the reference (_CCCL_NVTX_RANGE_SCOPE_IF(d_temp_storage, ...),
+  // device_radix_sort.cuh:424); costs nothing while no tool is attached
+  struct nvtx_scope
+  {
+    bool on;
+    explicit nvtx_scope(bool enable)
+        : on(enable)
+    {
+      if (on)
+      {
+        nvtxRangePushA("b200rs_sort");
+      }
+    }
+    ~nvtx_scope()
+    {
+      if (on)
+      {
+        nvtxRangePop();
+      }
+    }
+  } nvtx_range(d_temp_storage != nullptr);
   if (temp_storage_bytes == nullptr || key_kind < 0 || key_kind > 2)
   {
     return int(cudaErrorInvalidValue);

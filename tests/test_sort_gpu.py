@@ -501,3 +501,25 @@ def test_more_than_2_to_the_32_items(kb, extra):
     for lo in range(0, n - 1, chunk):
         a = kout[lo:lo + chunk + 1].to(torch.int32) & (nbins - 1)
         assert bool((a[1:] <= a[:-1]).all())
+
+
+def test_debug_sync_logging():
+    """B200RS_DEBUG_SYNC=1 (the counterpart of CUB_DEBUG_SYNC, cub/cub/util_debug.cuh:37-72): every stream operation of
+    the sort is synchronised and logged with its status; results are unchanged."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, 'tests');"
+        "from gen import make_keys; from gpu_util import gpu_sort; from oracle_lib import oracle_sort;"
+        "k = make_keys('uniform', 3_000_000, np.uint32, seed=1); g, _ = gpu_sort(k);"
+        "assert np.array_equal(g, oracle_sort(k)); print('ok')"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, B200RS_DEBUG_SYNC="1"),
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
+    for op in ("memset", "histogram", "scan", "onesweep"):
+        assert f"({op})" in res.stderr, res.stderr[-2000:]
+    assert res.stderr.count("(onesweep)") == 4 and "no error" in res.stderr
