@@ -18,6 +18,9 @@
 // kernel_segmented_radix_sort.cuh:213-272), so the -0.0 == +0.0 rule applies in the un-inverted domain at EVERY segment
 // size -- the rule make_xform calls single_tile_rule (pinned by tests/golden/segmented/cubseg_f32_*).
 #include "../../include/b200rs.h"
+#include "segmented_long.h"
+
+#include <atomic>
 #include "single_tile.cuh"
 
 namespace b200rs
@@ -39,6 +42,8 @@ struct SegArgs
   int end_bit;
   uint32_t all_ones;
   KeyXform xf;
+  const SegLongCtl* long_ctl; // != nullptr: segments longer than long_min are sorted by segmented_long.cu
+  uint32_t long_min;
 };
 
 __device__ __forceinline__ long long load_offset(const void* p, long long i, int bytes)
@@ -239,6 +244,10 @@ __global__ void __launch_bounds__(ST_THREADS, 3) segmented_sort_kernel(const Seg
     {
       continue;
     }
+    if (a.long_ctl != nullptr && len > (long long) a.long_min && a.long_ctl->overflow == 0)
+    {
+      continue; // whole-grid passes (segmented_long.cu)
+    }
     const U* kin = static_cast<const U*>(a.keys_in) + b;
     U* kout      = static_cast<U*>(a.keys_out) + b;
     const V* vin = VBYTES > 0 ? static_cast<const V*>(a.vals_in) + b : nullptr;
@@ -373,6 +382,56 @@ static cudaError_t launch_seg_v(int value_bytes, const SegArgs& a, int sms, cuda
 
 using namespace b200rs;
 
+static cudaError_t launch_seg_k(int key_bytes, int value_bytes, const SegArgs& a, int sms, cudaStream_t stream)
+{
+  switch (key_bytes)
+  {
+    case 1: return launch_seg_v<uint8_t>(value_bytes, a, sms, stream);
+    case 2: return launch_seg_v<uint16_t>(value_bytes, a, sms, stream);
+    case 4: return launch_seg_v<uint32_t>(value_bytes, a, sms, stream);
+    default: return launch_seg_v<uint64_t>(value_bytes, a, sms, stream);
+  }
+}
+
+// side stream + fork / join events of the calling host thread, one set per device (created on first use, kept)
+struct SideStream
+{
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+  bool made;
+};
+static SideStream* side_stream_of(int dev)
+{
+  static thread_local SideStream t_side[32] = {};
+  if (dev < 0 || dev >= 32)
+  {
+    return nullptr;
+  }
+  SideStream& s = t_side[dev];
+  if (!s.made)
+  {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess
+        || cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess)
+    {
+      (void) cudaGetLastError();
+      return nullptr;
+    }
+    s.made = true;
+  }
+  return &s;
+}
+
+// segments longer than this many items take the whole-grid passes (0 = never); a segment of at most one tile of the
+// per-segment kernel is always sorted in shared memory by one CTA whatever the value
+static std::atomic<uint32_t> g_seg_long_min{SEG_LONG_MIN_DEFAULT};
+
+extern "C" int b200rs_set_segmented_long_min(unsigned long long items)
+{
+  g_seg_long_min.store(items > 0xffffffffull ? 0xffffffffu : uint32_t(items), std::memory_order_relaxed);
+  return 0;
+}
+
 static size_t seg_align(size_t x)
 {
   return (x + 255) / 256 * 256;
@@ -419,7 +478,28 @@ extern "C" int b200rs_segmented_sort(
   // scratch copies for the passes of segments longer than one tile (the size query cannot know the segment sizes)
   const size_t off_keys = 0;
   const size_t off_vals = need_tmp ? seg_align(size_t(num_items) * key_bytes) : 0;
-  const size_t total    = need_tmp ? off_vals + seg_align(size_t(num_items) * value_bytes) + 255 : 1;
+  size_t total          = need_tmp ? off_vals + seg_align(size_t(num_items) * value_bytes) + 255 : 1;
+  // whole-grid passes for segments longer than long_min (segmented_long.cu): a table of at most
+  // num_items / long_min disjoint long segments, their bins and the chained-scan rows of all their tiles
+  uint32_t long_min = g_seg_long_min.load(std::memory_order_relaxed);
+  if (long_min != 0 && long_min < single_tile_capacity(key_bytes, value_bytes))
+  {
+    long_min = uint32_t(single_tile_capacity(key_bytes, value_bytes)); // one tile is sorted in shared memory, always
+  }
+  const bool use_long = long_min != 0 && passes > 0 && num_items > long_min && num_items < (1ull << 32)
+                     && seg_long_supported(key_bytes, value_bytes);
+  const uint32_t max_long    = use_long ? uint32_t(num_items / long_min) + 1u : 0u;
+  const uint32_t long_tile   = use_long ? seg_long_tile_items(key_bytes, value_bytes) : 1u;
+  const uint32_t tiles_bound = use_long ? uint32_t(num_items / long_tile) + max_long + 1u : 0u;
+  const size_t off_ctl  = seg_align(total);
+  const size_t off_tab  = off_ctl + seg_align(sizeof(SegLongCtl));
+  const size_t off_bins = off_tab + seg_align(size_t(max_long) * sizeof(SegLong));
+  const size_t off_lb   = off_bins + seg_align(size_t(max_long) * passes * RADIX * sizeof(unsigned long long));
+  const size_t lb_bytes = seg_align(size_t(tiles_bound) * RADIX * sizeof(uint32_t));
+  if (use_long)
+  {
+    total = off_lb + 2 * lb_bytes + 255;
+  }
   if (d_temp_storage == nullptr)
   {
     *temp_storage_bytes = total;
@@ -454,6 +534,8 @@ extern "C" int b200rs_segmented_sort(
   a.end_bit       = end_bit;
   a.all_ones      = 0xffffffffu;
   a.xf            = make_xform(key_kind, key_bytes, descending, /*single_tile_rule=*/true);
+  a.long_ctl      = use_long ? reinterpret_cast<const SegLongCtl*>(base + off_ctl) : nullptr;
+  a.long_min      = long_min;
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess)
@@ -464,11 +546,63 @@ extern "C" int b200rs_segmented_sort(
   {
     return int(e);
   }
-  switch (key_bytes)
+  if (use_long)
   {
-    case 1: return int(launch_seg_v<uint8_t>(value_bytes, a, sms, stream));
-    case 2: return int(launch_seg_v<uint16_t>(value_bytes, a, sms, stream));
-    case 4: return int(launch_seg_v<uint32_t>(value_bytes, a, sms, stream));
-    default: return int(launch_seg_v<uint64_t>(value_bytes, a, sms, stream));
+    // the long segments first: their table and overflow flag must exist before the per-segment kernel reads them
+    SegLongPlan p;
+    p.keys_in       = a.keys_in;
+    p.keys_out      = a.keys_out;
+    p.keys_tmp      = a.keys_tmp;
+    p.vals_in       = a.vals_in;
+    p.vals_out      = a.vals_out;
+    p.vals_tmp      = a.vals_tmp;
+    p.begin_offsets = a.begin_offsets;
+    p.end_offsets   = a.end_offsets;
+    p.num_segments  = a.num_segments;
+    p.offset_bytes  = a.offset_bytes;
+    p.begin_bit     = begin_bit;
+    p.end_bit       = end_bit;
+    p.passes        = passes;
+    p.xf            = a.xf;
+    p.ctl           = reinterpret_cast<SegLongCtl*>(base + off_ctl);
+    p.table         = reinterpret_cast<SegLong*>(base + off_tab);
+    p.bins          = reinterpret_cast<unsigned long long*>(base + off_bins);
+    p.lookback[0]   = reinterpret_cast<uint32_t*>(base + off_lb);
+    p.lookback[1]   = reinterpret_cast<uint32_t*>(base + off_lb + lb_bytes);
+    p.zero_bytes    = off_lb + lb_bytes - off_bins;
+    p.max_long      = max_long;
+    p.tiles_bound   = tiles_bound;
+    p.long_min      = long_min;
+    p.sms           = sms;
+    // The table of the long segments first (the per-segment kernel reads its overflow flag), then the two halves run
+    // side by side: the whole-grid passes on a side stream forked from the caller's stream, the per-segment kernel on
+    // the caller's stream, joined before returning.  With no long segment the side stream's (empty) launches hide behind
+    // the per-segment kernel; with both kinds the short segments fill the tails of the long passes.  Legal under capture.
+    e = seg_long_sort(p, 0, key_bytes, value_bytes, stream);
+    SideStream* side = e == cudaSuccess ? side_stream_of(dev) : nullptr;
+    if (e == cudaSuccess && side == nullptr)
+    {
+      e = seg_long_sort(p, 1, key_bytes, value_bytes, stream); // no side stream: everything in order on one stream
+    }
+    else if (e == cudaSuccess)
+    {
+      if ((e = cudaEventRecord(side->fork, stream)) == cudaSuccess
+          && (e = cudaStreamWaitEvent(side->stream, side->fork, 0)) == cudaSuccess)
+      {
+        e = seg_long_sort(p, 1, key_bytes, value_bytes, side->stream);
+      }
+      const cudaError_t e2 = launch_seg_k(key_bytes, value_bytes, a, sms, stream);
+      cudaError_t e3       = cudaEventRecord(side->join, side->stream);
+      if (e3 == cudaSuccess)
+      {
+        e3 = cudaStreamWaitEvent(stream, side->join, 0);
+      }
+      return int(e != cudaSuccess ? e : (e2 != cudaSuccess ? e2 : e3));
+    }
+    if (e != cudaSuccess)
+    {
+      return int(e);
+    }
   }
+  return int(launch_seg_k(key_bytes, value_bytes, a, sms, stream));
 }

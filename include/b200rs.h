@@ -480,6 +480,10 @@ B200RS_API int b200rs_set_single_tile(int on);
  * (items == ~0): up to 4 MiB of keys (2^20 4-byte / 2^19 8-byte keys, the measured break-even on B200); 0 sends
  * everything above one tile through the general multi-kernel path. */
 B200RS_API int b200rs_set_small_max(unsigned long long items);
+/* b200rs_segmented_sort: segments longer than this many items are sorted by whole-grid passes over all long segments at
+ * once, shorter ones by one CTA per segment (0 = always one CTA per segment).  Tuning / test hook, process-wide; the
+ * temp-storage query and the sort must see the same value. */
+B200RS_API int b200rs_set_segmented_long_min(unsigned long long items);
 
 /* Human-readable description of configuration `config_index` for (key_bytes, value_bytes); returns the number of
  * configurations available when config_index < 0.  buf may be NULL. */

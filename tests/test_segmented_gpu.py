@@ -140,3 +140,70 @@ def test_segments_in_any_order_and_unsorted_offsets():
     perm = np.array([2, 0, 4, 3, 1])
     k = make_keys("uniform", n, np.int32, seed=4)
     check(k, None, begins[perm], ends[perm])
+
+
+@pytest.mark.parametrize("kdtype,vdtype", [(np.uint32, None), (np.uint32, np.uint32), (np.float32, np.uint32), (np.uint64, None),
+                                           (np.int64, np.uint32), (np.float64, None), (np.uint32, np.uint64)])
+def test_long_segments_take_whole_grid_passes(kdtype, vdtype):
+    """Segments longer than 2^16 items are sorted by whole-grid onesweep passes over all long segments at once
+    (csrc/segmented_long.cu: tiles never straddle segments, per-segment bins and chained-scan rows); everything shorter
+    by one CTA per segment in the same call.  Long segments at both ends, next to each other, listed out of order, around
+    the threshold and around multiples of the tile; +-0.0; both directions; a bit window; (u32, u64) pairs take the
+    one-CTA path for every length (no whole-grid kernel for that width)."""
+    lengths = [70_000, 65_536, 65_537, -3, 100, 0, 200_003, 44 * 256 * 6, 1, 5000, 131_072 + 11_264, -17, 90_001]
+    begins, ends, n = layout(lengths)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(begins))
+    begins, ends = begins[perm], ends[perm]
+    for dist in ("uniform", "entropy3"):
+        k = make_keys(dist, n, kdtype, seed=31)
+        if np.dtype(kdtype).kind == "f":
+            k[::5] = -0.0
+            k[::7] = 0.0
+        v = make_values(n, vdtype) if vdtype is not None else None
+        bits = np.dtype(kdtype).itemsize * 8
+        check(k, v, begins, ends)
+        check(k, v, begins, ends, descending=True, offset_dtype=np.int32)
+        check(k, v, begins, ends, descending=(dist == "uniform"), begin_bit=5, end_bit=bits - 9)
+        check(k, v, begins, ends, begin_bit=bits - 3, end_bit=bits)
+
+
+def test_long_segments_all_equal_and_single_huge():
+    begins, ends, n = layout([(1 << 21) + 77])
+    k = make_keys("equal", n, np.uint32, seed=1)
+    check(k, make_values(n, np.uint32), begins, ends)
+    k = make_keys("few16", n, np.uint64, seed=2)
+    check(k, make_values(n, np.uint32), begins, ends, descending=True)
+    k = make_keys("uniform", n, np.uint32, seed=3)
+    check(k, None, begins, ends)
+
+
+def test_segmented_sort_under_stream_capture_with_long_segments():
+    """The two halves of a call (whole-grid passes for long segments on a forked side stream, one CTA per short segment on
+    the caller's stream) are joined on the caller's stream: the call is one capturable unit of work."""
+    lib = _native.lib()
+    begins, ends, n = layout([100_000, 300, 0, 70_000, 4000, 9])
+    k = make_keys("uniform", n, np.uint32, seed=8)
+    v = make_values(n, np.uint32)
+    check(k, v, begins, ends)  # warm: the side stream exists before the capture below
+    d_k, d_v = to_dev(k), to_dev(v)
+    d_ko, d_vo = d_k.clone(), d_v.clone()
+    d_b, d_e = to_dev(begins), to_dev(ends)
+    nbytes = ctypes.c_size_t(0)
+    tail = (n, len(begins), d_b.data_ptr(), d_e.data_ptr(), 8, 0, 4, 4, 0, 32, 0)
+    _native.check(lib.b200rs_segmented_sort(None, ctypes.byref(nbytes), None, None, None, None, *tail, 0), "query")
+    temp = torch.empty(nbytes.value + 256, dtype=torch.uint8, device="cuda")
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        st = torch.cuda.current_stream().cuda_stream
+        _native.check(lib.b200rs_segmented_sort(temp.data_ptr(), ctypes.byref(nbytes), d_k.data_ptr(), d_ko.data_ptr(),
+                                                d_v.data_ptr(), d_vo.data_ptr(), *tail, st), "segmented sort under capture")
+    ek, ev = oracle_segmented_sort(k, v, begins, ends)
+    for _ in range(2):
+        d_ko.zero_()
+        d_vo.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for b, e in zip(begins.tolist(), ends.tolist()):
+            assert_same_bits(to_host(d_ko, np.uint32, n)[b:e], ek[b:e], "captured segmented keys")
+            assert_same_bits(to_host(d_vo, np.uint32, n)[b:e], ev[b:e], "captured segmented values")

@@ -30,6 +30,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "segmented_bench.jsonl"))
     ap.add_argument("--log2n", type=int, default=24)
+    ap.add_argument("--long-min", type=int, nargs="*", default=None,
+                    help="sweep b200rs_set_segmented_long_min over these values (0 = one CTA per segment always)")
+    ap.add_argument("--means", type=int, nargs="*", default=[100, 1000, 20000, 1 << 20])
     args = ap.parse_args()
     lib = _native.lib()
     n = 1 << args.log2n
@@ -38,7 +41,7 @@ def main():
     vals = np.arange(n, dtype=np.uint32)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f, tempfile.TemporaryDirectory() as d:
-        for mean in (100, 1000, 20000, 1 << 20):
+        for mean in args.means:
             lens = rng.integers(0, 2 * mean + 1, size=max(2, 2 * n // mean)).astype(np.int64)
             ends = np.cumsum(lens)
             ends = ends[ends <= n]
@@ -49,6 +52,28 @@ def main():
             db, de = torch.from_numpy(begins).cuda(), torch.from_numpy(ends.astype(np.int64)).cuda()
             st = torch.cuda.current_stream().cuda_stream
             a = (n, segs, db.data_ptr(), de.data_ptr(), 8, 0, 4, 4, 0, 32, 0, st)
+            if args.long_min:  # threshold sweep: our side only
+                for lm in args.long_min:
+                    lib.b200rs_set_segmented_long_min(lm)
+                    nb = ctypes.c_size_t(0)
+                    _native.check(lib.b200rs_segmented_sort(None, ctypes.byref(nb), None, None, None, None, *a), "query")
+                    temp = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
+                    run = lambda: _native.check(lib.b200rs_segmented_sort(
+                        temp.data_ptr(), ctypes.byref(nb), dk.data_ptr(), ko.data_ptr(), dv.data_ptr(), vo.data_ptr(), *a), "sort")
+                    for _ in range(3):
+                        run()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for _ in range(20):
+                        run()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    rec = {"mean_segment": mean, "long_min": lm, "ms": e0.elapsed_time(e1) / 20, "temp_bytes": nb.value}
+                    print(json.dumps(rec), flush=True)
+                    f.write(json.dumps(rec) + "\n")
+                lib.b200rs_set_segmented_long_min(1 << 16)
+                continue
             nb = ctypes.c_size_t(0)
             _native.check(lib.b200rs_segmented_sort(None, ctypes.byref(nb), None, None, None, None, *a), "query")
             temp = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
