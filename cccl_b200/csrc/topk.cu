@@ -15,6 +15,11 @@
 #include "../../include/b200rs.h"
 #include "common.cuh"
 
+#include <atomic>
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
 namespace b200rs
 {
 
@@ -128,15 +133,12 @@ __device__ __forceinline__ uint32_t topk_block_scan(uint32_t v, uint32_t* warp_s
 // all its selected items (and one more hands out tie tickets, only while ties are still needed and present), so the two
 // global counters see n / 2048 atomics instead of one per warp row (k = 2^23 of 2^28: 4.2 -> ms).
 template <class U, int VBYTES>
-__global__ void __launch_bounds__(TOPK_THREADS)
-topk_filter_kernel(const U* keys, U* keys_out, const typename value_of<VBYTES>::type* vals,
-                   typename value_of<VBYTES>::type* vals_out, unsigned long long n, const KeyXform kx, TopkState* st)
+__device__ __forceinline__ void
+topk_filter_body(const U* keys, U* keys_out, const typename value_of<VBYTES>::type* vals,
+                 typename value_of<VBYTES>::type* vals_out, unsigned long long n, const KeyXform& kx, TopkState* st,
+                 const U kth, const unsigned long long need_eq, uint32_t* warp_sums, unsigned long long* s_base)
 {
-  __shared__ uint32_t warp_sums[TOPK_THREADS / 32];
-  __shared__ unsigned long long s_base[2];
   const XformT<U> xf(kx);
-  const U kth                      = U(st->prefix);
-  const unsigned long long need_eq = st->need_eq;
   constexpr unsigned long long CHUNK = (unsigned long long) TOPK_THREADS * TOPK_ITEMS;
   for (unsigned long long base = (unsigned long long) blockIdx.x * CHUNK; base < n;
        base += (unsigned long long) gridDim.x * CHUNK)
@@ -205,6 +207,148 @@ topk_filter_kernel(const U* keys, U* keys_out, const typename value_of<VBYTES>::
   }
 }
 
+template <class U, int VBYTES>
+__global__ void __launch_bounds__(TOPK_THREADS)
+topk_filter_kernel(const U* keys, U* keys_out, const typename value_of<VBYTES>::type* vals,
+                   typename value_of<VBYTES>::type* vals_out, unsigned long long n, const KeyXform kx, TopkState* st)
+{
+  __shared__ uint32_t warp_sums[TOPK_THREADS / 32];
+  __shared__ unsigned long long s_base[2];
+  topk_filter_body<U, VBYTES>(keys, keys_out, vals, vals_out, n, kx, st, U(st->prefix), st->need_eq, warp_sums, s_base);
+}
+
+// Small inputs: the whole selection in ONE cooperative launch.  Below a few million keys every kernel of the select is
+// shorter than the gap between two launches (11 stream operations ~ 60 us); here the same rounds run between grid-wide
+// barriers: zero | per digit, most significant first: every CTA histograms the next digit of the keys that carry the
+// prefix chosen so far (all keys, they are L2-resident at this size) and, after the barrier, picks the bin holding rank
+// K from the grid-wide counts itself (every CTA computes the same answer: no second barrier) | filter.
+struct TopkSmallArgs
+{
+  const void* keys;
+  void* keys_out;
+  const void* vals;
+  void* vals_out;
+  unsigned long long n, k;
+  KeyXform xf;
+  TopkState* st;
+  unsigned int* hist; // [key bytes][256], zeroed by the kernel
+};
+
+template <class U, int VBYTES>
+__global__ void __launch_bounds__(TOPK_THREADS) topk_small_kernel(const TopkSmallArgs a)
+{
+  using V = typename value_of<VBYTES>::type;
+  __shared__ uint32_t sh[RADIX];
+  __shared__ uint32_t warp_sums[TOPK_THREADS / 32];
+  __shared__ unsigned long long s_base[2];
+  __shared__ unsigned long long s_pick[2]; // chosen bin, keys before it
+  cg::grid_group grid = cg::this_grid();
+  constexpr int ROUNDS = int(sizeof(U));
+  constexpr int BITS   = ROUNDS * 8;
+  const XformT<U> xf(a.xf);
+  const U* keys              = static_cast<const U*>(a.keys);
+  const unsigned long long n = a.n;
+  const uint32_t gtid = blockIdx.x * TOPK_THREADS + threadIdx.x, gsize = gridDim.x * TOPK_THREADS;
+  for (uint32_t i = gtid; i < uint32_t(ROUNDS) * RADIX; i += gsize)
+  {
+    a.hist[i] = 0;
+  }
+  if (gtid == 0)
+  {
+    a.st->out_count = 0;
+    a.st->eq_taken  = 0;
+  }
+  grid.sync();
+  unsigned long long prefix = 0, below = 0;
+  for (int r = 0; r < ROUNDS; ++r)
+  {
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int lo_shift = BITS - 8 * (r + 1);
+    // four independent loads in flight per thread (eight, and twice the CTAs: measured slower, r4q) (the keys are L2-resident: the scan is latency-bound otherwise; a
+    // 32-way replicated histogram was measured too -- slower: zeroing and folding 32 KB per round costs more than the
+    // bank conflicts of round 0, profiles/r4o_topk_small_sweep.jsonl)
+    for (unsigned long long i0 = gtid; i0 < n; i0 += 4ull * gsize)
+    {
+      U raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        const unsigned long long i = i0 + (unsigned long long) u * gsize;
+        raw[u]                     = i < n ? keys[i] : U(0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        const unsigned long long i = i0 + (unsigned long long) u * gsize;
+        const U t                  = digit_view(twiddle_in(raw[u], xf), xf);
+        // r == 0: every key carries the (empty) prefix; a shift by the full width is avoided
+        if (i < n && (r == 0 || (unsigned long long) (t >> (lo_shift + 8)) == prefix))
+        {
+          atomicAdd(&sh[(unsigned int) (t >> lo_shift) & (RADIX - 1)], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    if (sh[threadIdx.x] != 0)
+    {
+      atomicAdd(&a.hist[r * RADIX + threadIdx.x], sh[threadIdx.x]);
+    }
+    grid.sync();
+    // pick: first bin whose running count reaches the remaining rank (256 threads: one bin each)
+    {
+      const uint32_t c = a.hist[r * RADIX + threadIdx.x];
+      uint32_t total;
+      const uint32_t before = topk_block_scan(c, warp_sums, total);
+      const unsigned long long want = a.k - below; // >= 1
+      if (before < want && want <= (unsigned long long) before + c)
+      {
+        s_pick[0] = threadIdx.x;
+        s_pick[1] = before;
+      }
+      __syncthreads();
+      prefix = prefix * RADIX + s_pick[0];
+      below += s_pick[1];
+      __syncthreads();
+    }
+  }
+  topk_filter_body<U, VBYTES>(keys, static_cast<U*>(a.keys_out), static_cast<const V*>(a.vals), static_cast<V*>(a.vals_out),
+                              n, a.xf, a.st, U(prefix), a.k - below, warp_sums, s_base);
+}
+
+template <class U, int VB>
+static cudaError_t launch_topk_small(const TopkSmallArgs& a, int sms, cudaStream_t stream)
+{
+  auto kernel = topk_small_kernel<U, VB>;
+  int per_sm  = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TOPK_THREADS, 0);
+  if (e != cudaSuccess)
+  {
+    return e;
+  }
+  // every CTA must be resident; few CTAs make the barriers cheap: about 4096 keys per CTA and round
+  unsigned long long want = (a.n + 4095) / 4096;
+  const unsigned long long cap = (unsigned long long) sms * (per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm));
+  const unsigned grid          = unsigned(want < 1 ? 1 : (want < cap ? want : cap));
+  void* params[]               = {const_cast<TopkSmallArgs*>(&a)};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(TOPK_THREADS), params, 0, stream);
+}
+
+template <class U>
+static cudaError_t launch_topk_small_v(int vb, const TopkSmallArgs& a, int sms, cudaStream_t stream)
+{
+  switch (vb)
+  {
+    case 0: return launch_topk_small<U, 0>(a, sms, stream);
+    case 1: return launch_topk_small<U, 1>(a, sms, stream);
+    case 2: return launch_topk_small<U, 2>(a, sms, stream);
+    case 4: return launch_topk_small<U, 4>(a, sms, stream);
+    case 8: return launch_topk_small<U, 8>(a, sms, stream);
+    case 16: return launch_topk_small<U, 16>(a, sms, stream);
+    default: return cudaErrorNotSupported;
+  }
+}
+
 template <class U, int VB>
 static cudaError_t launch_filter(const void* keys, void* keys_out, const void* vals, void* vals_out, unsigned long long n,
                                  const KeyXform& xf, TopkState* st, int sms, cudaStream_t stream)
@@ -238,6 +382,16 @@ static cudaError_t launch_filter_v(int vb, const void* keys, void* keys_out, con
 } // namespace b200rs
 
 using namespace b200rs;
+
+// inputs of at most this many key bytes (2^23 4-byte keys) take the one-launch kernel (b200rs_set_topk_small_max
+// overrides, 0 = never)
+static std::atomic<unsigned long long> g_topk_small_max_bytes{32ull << 20}; // measured crossover, profiles/r4p_*
+
+extern "C" int b200rs_set_topk_small_max(unsigned long long key_bytes_total)
+{
+  g_topk_small_max_bytes.store(key_bytes_total, std::memory_order_relaxed);
+  return 0;
+}
 
 static size_t t_align(size_t x)
 {
@@ -306,6 +460,37 @@ extern "C" int b200rs_topk(
   unsigned char* base = reinterpret_cast<unsigned char*>(t_align(reinterpret_cast<size_t>(d_temp_storage)));
   TopkState* st       = reinterpret_cast<TopkState*>(base + off_state);
   uint64_t* hist      = reinterpret_cast<uint64_t*>(base + off_hist);
+  if (num_items * uint64_t(key_bytes) <= g_topk_small_max_bytes.load(std::memory_order_relaxed))
+  {
+    // one cooperative launch (the 256 * 8-byte histogram area of the general path holds key_bytes * 256 u32 counters)
+    int dev0 = 0, sms0 = 0;
+    e = cudaGetDevice(&dev0);
+    if (e == cudaSuccess)
+    {
+      e = cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+    }
+    if (e != cudaSuccess)
+    {
+      return int(e);
+    }
+    TopkSmallArgs sa;
+    sa.keys     = d_keys_in;
+    sa.keys_out = d_keys_out;
+    sa.vals     = d_values_in;
+    sa.vals_out = d_values_out;
+    sa.n        = num_items;
+    sa.k        = k;
+    sa.xf       = make_xform(key_kind, key_bytes, largest ? 1 : 0);
+    sa.st       = st;
+    sa.hist     = reinterpret_cast<unsigned int*>(hist);
+    switch (key_bytes)
+    {
+      case 1: return int(launch_topk_small_v<uint8_t>(value_bytes, sa, sms0, stream));
+      case 2: return int(launch_topk_small_v<uint16_t>(value_bytes, sa, sms0, stream));
+      case 4: return int(launch_topk_small_v<uint32_t>(value_bytes, sa, sms0, stream));
+      default: return int(launch_topk_small_v<uint64_t>(value_bytes, sa, sms0, stream));
+    }
+  }
   uint64_t* cstate    = reinterpret_cast<uint64_t*>(base + off_cstate);
   void* cand          = base + off_cand;
   // "largest" = the first K of the DESCENDING order: the kernels' own descending transform

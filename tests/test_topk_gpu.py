@@ -63,9 +63,19 @@ def check(keys, k, largest, with_values, **kw):
 KEY_DTYPES = [np.uint8, np.int16, np.float16, np.uint32, np.int32, np.float32, np.uint64, np.int64, np.float64]
 
 
+@pytest.fixture(params=["one_launch", "general"])
+def topk_path(request):
+    """Inputs of at most 32 MiB of keys take the one-launch cooperative kernel by default; "general" switches it off so that
+    the same cases also run the multi-kernel radix select (candidate compaction included)."""
+    lib = _native.lib()
+    lib.b200rs_set_topk_small_max(0 if request.param == "general" else 32 << 20)
+    yield request.param
+    lib.b200rs_set_topk_small_max(32 << 20)
+
+
 @pytest.mark.parametrize("dtype", KEY_DTYPES)
 @pytest.mark.parametrize("largest", [False, True])
-def test_topk_sizes_and_k(dtype, largest):
+def test_topk_sizes_and_k(dtype, largest, topk_path):
     for n in (1, 2, 33, 1000, 70_001, (1 << 20) + 3):
         keys = make_keys("uniform", n, dtype, seed=n)
         if np.dtype(dtype).kind == "f" and n > 40:
@@ -79,7 +89,7 @@ def test_topk_sizes_and_k(dtype, largest):
 
 @pytest.mark.parametrize("dist", ["equal", "few2", "few16", "entropy5", "sorted", "reverse"])
 @pytest.mark.parametrize("dtype", [np.uint32, np.float32, np.int64])
-def test_topk_ties_and_skew(dist, dtype):
+def test_topk_ties_and_skew(dist, dtype, topk_path):
     """Many keys tied with the K-th one: exactly K items come back, every index once."""
     n = 300_007
     keys = make_keys(dist, n, dtype, seed=5)
@@ -88,7 +98,7 @@ def test_topk_ties_and_skew(dist, dtype):
         check(keys, k, False, True)
 
 
-def test_topk_float_specials():
+def test_topk_float_specials(topk_path):
     n = 50_000
     keys = make_keys("uniform", n, np.float32, seed=9)
     keys[:100] = np.nan
@@ -102,7 +112,7 @@ def test_topk_float_specials():
 
 
 @pytest.mark.parametrize("vdtype", [np.uint8, np.uint16, np.uint32, np.uint64])
-def test_topk_value_widths(vdtype):
+def test_topk_value_widths(vdtype, topk_path):
     n = 200 if vdtype == np.uint8 else 40_000
     keys = make_keys("uniform", n, np.uint32, seed=3)
     check(keys, n // 4, True, True, vdtype=vdtype)
@@ -130,7 +140,7 @@ def test_topk_edge_cases():
     assert lib.b200rs_topk(0, ctypes.byref(need), 0, 0, 0, 0, 10, 1, 0, 4, 12, 1, 0) == 801
 
 
-def test_topk_on_side_stream_and_capture():
+def test_topk_on_side_stream_and_capture(topk_path):
     """Enqueued on the caller's stream without synchronising: legal inside a CUDA graph."""
     keys = make_keys("uniform", 100_000, np.uint32, seed=1)
     s = torch.cuda.Stream()
@@ -196,7 +206,7 @@ TOPK_KT = {np.dtype(np.uint32): "u32", np.dtype(np.int32): "i32", np.dtype(np.fl
     (np.int64, "few256", 1 << 20, 50_000, False),
     (np.float64, "uniform", 200_003, 100_000, True),
 ])
-def test_topk_same_selection_as_reference_cub(dtype, dist, n, k, largest):
+def test_topk_same_selection_as_reference_cub(dtype, dist, n, k, largest, topk_path):
     """Both return the K best keys in unspecified order: as sorted multisets they must be identical."""
     keys = make_keys(dist, n, dtype, seed=21)
     if np.dtype(dtype).kind == "f":

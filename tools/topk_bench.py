@@ -54,7 +54,17 @@ def cub(log2n, log2k, and_rounds, iters=20):
 
 
 if __name__ == "__main__":
-    for log2n in (20, 24, 28):
+    if len(sys.argv) > 1 and sys.argv[1] == "--small-sweep":
+        # one-launch kernel vs the multi-kernel select around the crossover (ours only)
+        for log2n in (20, 21, 22, 23, 24, 25, 26):
+            for log2k in (11, 19):
+                row = {"workload": f"topk_u32_2^{log2n}_k2^{log2k}"}
+                for name, mx in (("general", 0), ("one_launch", 1 << 40)):
+                    _native.lib().b200rs_set_topk_small_max(mx)
+                    row[name + "_ms"] = ours(log2n, log2k, 1)["ms"]
+                print(json.dumps(row), flush=True)
+        sys.exit(0)
+    for log2n in (16, 20, 22, 24, 28):
         for log2k in (3, 11, 19, 23):
             if log2k >= log2n:
                 continue
