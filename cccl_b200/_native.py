@@ -41,6 +41,7 @@ EXPORTS = (
     "b200rs_set_single_tile",
     "b200rs_set_small_max",
     "b200rs_set_segmented_long_min",
+    "b200rs_set_segmented_tiny_max",
     "b200rs_set_topk_small_max",
     "b200rs_describe_config",
     "b200rs_timing_enable",
@@ -140,6 +141,8 @@ def lib() -> ctypes.CDLL:
         l.b200rs_set_small_max.argtypes = [ctypes.c_ulonglong]
         l.b200rs_set_segmented_long_min.restype = i32
         l.b200rs_set_segmented_long_min.argtypes = [ctypes.c_ulonglong]
+        l.b200rs_set_segmented_tiny_max.restype = i32
+        l.b200rs_set_segmented_tiny_max.argtypes = [ctypes.c_ulonglong]
         l.b200rs_set_topk_small_max.restype = i32
         l.b200rs_set_topk_small_max.argtypes = [ctypes.c_ulonglong]
         l.b200rs_set_single_tile.restype = i32

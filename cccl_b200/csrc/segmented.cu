@@ -44,6 +44,7 @@ struct SegArgs
   KeyXform xf;
   const SegLongCtl* long_ctl; // != nullptr: segments longer than long_min are sorted by segmented_long.cu
   uint32_t long_min;
+  uint32_t tiny_max; // segments of at most this many items are sorted by segmented_tiny_kernel (0 = none)
 };
 
 __device__ __forceinline__ long long load_offset(const void* p, long long i, int bytes)
@@ -248,6 +249,10 @@ __global__ void __launch_bounds__(ST_THREADS, 3) segmented_sort_kernel(const Seg
     {
       continue; // whole-grid passes (segmented_long.cu)
     }
+    if (len <= (long long) a.tiny_max)
+    {
+      continue; // one warp per segment (segmented_tiny_kernel)
+    }
     const U* kin = static_cast<const U*>(a.keys_in) + b;
     U* kout      = static_cast<U*>(a.keys_out) + b;
     const V* vin = VBYTES > 0 ? static_cast<const V*>(a.vals_in) + b : nullptr;
@@ -337,6 +342,192 @@ __global__ void __launch_bounds__(ST_THREADS, 3) segmented_sort_kernel(const Seg
   }
 }
 
+// Tiny segments: ONE WARP per segment of at most TINY_ROWS * 32 items.  A 256-thread CTA per 100-item segment is mostly
+// overhead (barriers, 8 warps' counter tables, a 256-digit block scan per pass); here a warp keeps the segment in
+// registers (item j * 32 + lane in slot j), ranks every 8-bit pass with the same match-by-ballot code against ONE
+// 256-entry counter table, scans the table itself (8 digits per lane) and permutes through a private staging area.
+// No block-wide barrier anywhere; items past the end never take part (their lanes are masked out of the ballots).
+constexpr int TINY_ROWS  = 8;
+constexpr int TINY_WARPS = 4; // per CTA
+
+template <class U, int VBYTES, bool FLOATK>
+__global__ void __launch_bounds__(TINY_WARPS * 32) segmented_tiny_kernel(const SegArgs a)
+{
+  using V = typename value_of<VBYTES>::type;
+  constexpr int ITEM = int(sizeof(U)) > VBYTES ? int(sizeof(U)) : VBYTES;
+  __shared__ uint32_t s_cnt[TINY_WARPS][RADIX];
+  __shared__ __align__(16) unsigned char s_stage[TINY_WARPS][TINY_ROWS * 32 * ITEM];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* cnt       = s_cnt[warp];
+  U* stage_k          = reinterpret_cast<U*>(s_stage[warp]);
+  V* stage_v          = reinterpret_cast<V*>(s_stage[warp]);
+  const XformT<U> xf(a.xf);
+  const U neg_zero = U(a.xf.neg_zero), pos_zero = U(a.xf.pos_zero);
+  const uint32_t lt_mask = lanemask_lt();
+  const int passes       = (a.end_bit - a.begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+  const long long nwarps = (long long) gridDim.x * TINY_WARPS;
+  for (long long seg = (long long) blockIdx.x * TINY_WARPS + warp; seg < a.num_segments; seg += nwarps)
+  {
+    const long long b   = load_offset(a.begin_offsets, seg, a.offset_bytes);
+    const long long e   = load_offset(a.end_offsets, seg, a.offset_bytes);
+    const long long len = a.offset_bytes == 8 ? e - b : (long long) (int) (uint32_t(e) - uint32_t(b));
+    if (len <= 0 || len > (long long) a.tiny_max)
+    {
+      continue;
+    }
+    const uint32_t n    = uint32_t(len);
+    const uint32_t rows = (n + 31) / 32; // warp-uniform
+    const U* kin = static_cast<const U*>(a.keys_in) + b;
+    U* kout      = static_cast<U*>(a.keys_out) + b;
+    U key[TINY_ROWS];
+    V val[VBYTES > 0 ? TINY_ROWS : 1];
+#pragma unroll
+    for (int j = 0; j < TINY_ROWS; ++j)
+    {
+      const uint32_t i = j * 32 + lane;
+      if (i < n)
+      {
+        key[j] = twiddle_in(kin[i], xf);
+        if (VBYTES > 0)
+        {
+          val[j] = static_cast<const V*>(a.vals_in)[b + i];
+        }
+      }
+    }
+    for (int p = 0; p < passes; ++p)
+    {
+      const int bit       = a.begin_bit + p * RADIX_BITS;
+      const int nbits     = (a.end_bit - bit) < RADIX_BITS ? (a.end_bit - bit) : RADIX_BITS;
+      const uint32_t mask = (1u << nbits) - 1u;
+#pragma unroll
+      for (int q = 0; q < RADIX / 32; ++q)
+      {
+        cnt[q * 32 + lane] = 0;
+      }
+      __syncwarp();
+      uint32_t rank[TINY_ROWS];
+#pragma unroll
+      for (int j = 0; j < TINY_ROWS; ++j)
+      {
+        if (uint32_t(j) < rows)
+        {
+          const bool valid    = uint32_t(j) * 32 + lane < n;
+          const uint32_t d    = valid ? pass_digit<FLOATK>(key[j], bit, mask, neg_zero, pos_zero) : 0u;
+          const uint32_t live = __ballot_sync(0xffffffffu, valid);
+          uint32_t mb, mc;
+          match_digit_ballot(d, mb, mc);
+          const uint32_t peers = mb & mc & live;
+          if (valid)
+          {
+            const uint32_t old = cnt[d];
+            rank[j]            = old + uint32_t(__popc(peers & lt_mask));
+            if ((peers >> lane) >> 1 == 0) // highest peer lane: the new running count
+            {
+              cnt[d] = old + uint32_t(__popc(peers));
+            }
+          }
+          __syncwarp();
+        }
+      }
+      // exclusive scan of the 256 counts: lane l owns digits 8l .. 8l + 7
+      {
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+        {
+          c[q] = cnt[lane * 8 + q];
+          sum += c[q];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1)
+        {
+          const uint32_t up = __shfl_up_sync(0xffffffffu, incl, sft);
+          incl += lane >= uint32_t(sft) ? up : 0u;
+        }
+        uint32_t run = incl - sum;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+        {
+          cnt[lane * 8 + q] = run;
+          run += c[q];
+        }
+      }
+      __syncwarp();
+      // permute: keys (then values) through the staging area
+#pragma unroll
+      for (int j = 0; j < TINY_ROWS; ++j)
+      {
+        if (uint32_t(j) * 32 + lane < n)
+        {
+          rank[j] += cnt[pass_digit<FLOATK>(key[j], bit, mask, neg_zero, pos_zero)];
+          stage_k[rank[j]] = key[j];
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < TINY_ROWS; ++j)
+      {
+        if (uint32_t(j) * 32 + lane < n)
+        {
+          key[j] = stage_k[j * 32 + lane];
+        }
+      }
+      if (VBYTES > 0)
+      {
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < TINY_ROWS; ++j)
+        {
+          if (uint32_t(j) * 32 + lane < n)
+          {
+            stage_v[rank[j]] = val[j];
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < TINY_ROWS; ++j)
+        {
+          if (uint32_t(j) * 32 + lane < n)
+          {
+            val[j] = stage_v[j * 32 + lane];
+          }
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < TINY_ROWS; ++j)
+    {
+      const uint32_t i = j * 32 + lane;
+      if (i < n)
+      {
+        kout[i] = twiddle_out(key[j], xf);
+        if (VBYTES > 0)
+        {
+          static_cast<V*>(a.vals_out)[b + i] = val[j];
+        }
+      }
+    }
+  }
+}
+
+template <class U, int VB>
+static cudaError_t launch_seg_tiny(const SegArgs& a, int sms, cudaStream_t stream)
+{
+  constexpr bool CAN_FLOAT = sizeof(U) >= 2;
+  auto kernel              = segmented_tiny_kernel<U, VB, false>;
+  if (CAN_FLOAT && a.xf.float_mask != 0)
+  {
+    kernel = segmented_tiny_kernel<U, VB, CAN_FLOAT>;
+  }
+  const long long want = (a.num_segments + TINY_WARPS - 1) / TINY_WARPS;
+  const long long cap  = (long long) sms * 32;
+  kernel<<<unsigned(want < cap ? want : cap), TINY_WARPS * 32, 0, stream>>>(a);
+  return cudaPeekAtLastError();
+}
+
 template <class U, int VB>
 static cudaError_t launch_seg(const SegArgs& a, int sms, cudaStream_t stream)
 {
@@ -351,6 +542,14 @@ static cudaError_t launch_seg(const SegArgs& a, int sms, cudaStream_t stream)
   if (L::BYTES > 32 * 1024) // static shared memory (offsets + all-pass histograms) comes on top
   {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(L::BYTES));
+    if (e != cudaSuccess)
+    {
+      return e;
+    }
+  }
+  if (a.tiny_max != 0)
+  {
+    cudaError_t e = launch_seg_tiny<U, VB>(a, sms, stream);
     if (e != cudaSuccess)
     {
       return e;
@@ -425,6 +624,15 @@ static SideStream* side_stream_of(int dev)
 // segments longer than this many items take the whole-grid passes (0 = never); a segment of at most one tile of the
 // per-segment kernel is always sorted in shared memory by one CTA whatever the value
 static std::atomic<uint32_t> g_seg_long_min{SEG_LONG_MIN_DEFAULT};
+
+// segments of at most this many items are sorted by one warp each (at most TINY_ROWS * 32; 0 = never)
+static std::atomic<uint32_t> g_seg_tiny_max{TINY_ROWS * 32};
+
+extern "C" int b200rs_set_segmented_tiny_max(unsigned long long items)
+{
+  g_seg_tiny_max.store(items > TINY_ROWS * 32 ? uint32_t(TINY_ROWS * 32) : uint32_t(items), std::memory_order_relaxed);
+  return 0;
+}
 
 extern "C" int b200rs_set_segmented_long_min(unsigned long long items)
 {
@@ -536,6 +744,7 @@ extern "C" int b200rs_segmented_sort(
   a.xf            = make_xform(key_kind, key_bytes, descending, /*single_tile_rule=*/true);
   a.long_ctl      = use_long ? reinterpret_cast<const SegLongCtl*>(base + off_ctl) : nullptr;
   a.long_min      = long_min;
+  a.tiny_max      = g_seg_tiny_max.load(std::memory_order_relaxed);
   int dev = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess)

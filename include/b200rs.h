@@ -484,6 +484,9 @@ B200RS_API int b200rs_set_small_max(unsigned long long items);
  * once, shorter ones by one CTA per segment (0 = always one CTA per segment).  Tuning / test hook, process-wide; the
  * temp-storage query and the sort must see the same value. */
 B200RS_API int b200rs_set_segmented_long_min(unsigned long long items);
+/* b200rs_segmented_sort: segments of at most this many items (at most 256) are sorted by one warp each instead of one
+ * CTA each; 0 = never.  Tuning / test hook, process-wide. */
+B200RS_API int b200rs_set_segmented_tiny_max(unsigned long long items);
 /* b200rs_topk: inputs of at most this many BYTES of keys are selected by one cooperative launch (the rounds of the radix
  * select between grid-wide barriers) instead of one launch per round; default 32 MiB (the measured crossover on B200), 0 = never.  Tuning / test hook. */
 B200RS_API int b200rs_set_topk_small_max(unsigned long long key_bytes_total);

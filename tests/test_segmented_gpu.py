@@ -47,6 +47,16 @@ def gpu_segmented_sort(keys, values, begins, ends, *, descending=False, begin_bi
     return gk, gv
 
 
+@pytest.fixture(params=["warp_per_tiny_segment", "cta_per_segment"])
+def tiny_path(request):
+    """Segments of at most 256 items are sorted by one warp each by default; "cta_per_segment" switches that off so the same
+    cases also run the one-CTA-per-segment kernel on them."""
+    lib = _native.lib()
+    lib.b200rs_set_segmented_tiny_max(0 if request.param == "cta_per_segment" else 256)
+    yield request.param
+    lib.b200rs_set_segmented_tiny_max(256)
+
+
 def layout(lengths):
     begins, ends, pos = [], [], 0
     for ln in lengths:
@@ -88,8 +98,9 @@ def test_real_cub_segmented_fixtures():
 
 @pytest.mark.parametrize("kdtype", [np.uint8, np.int16, np.float16, np.uint32, np.int32, np.float32, np.uint64, np.float64])
 @pytest.mark.parametrize("descending", [False, True])
-def test_segment_shapes_all_key_types(kdtype, descending):
-    lengths = [0, 1, 2, -3, 31, 32, 33, 0, 255, 1279, 1280, 1281, -1, 2560, 2561, 5119, 5120, 5121, 7000, -11, 20_011, 3]
+def test_segment_shapes_all_key_types(kdtype, descending, tiny_path):
+    lengths = [0, 1, 2, -3, 31, 32, 33, 0, 63, 64, 65, 100, 255, 256, 257, 1279, 1280, 1281, -1, 2560, 2561, 5119, 5120, 5121, 7000,
+               -11, 20_011, 3, 129, 200, 7, 96]
     begins, ends, n = layout(lengths)
     k = make_keys("uniform", n, kdtype, seed=77)
     if np.dtype(kdtype).kind == "f":
@@ -100,8 +111,8 @@ def test_segment_shapes_all_key_types(kdtype, descending):
 
 
 @pytest.mark.parametrize("vdtype", [np.uint8, np.uint16, np.uint64, V16])
-def test_value_widths_and_stability(vdtype):
-    lengths = [300, 6000, 0, 14_000, -5, 1]
+def test_value_widths_and_stability(vdtype, tiny_path):
+    lengths = [300, 6000, 0, 14_000, -5, 1, 250, 33, 128, 17]
     begins, ends, n = layout(lengths)
     for kdtype in (np.uint32, np.uint64):
         k = make_keys("few16", n, kdtype, seed=5)  # many ties inside every segment: stability is visible in the values
@@ -110,8 +121,8 @@ def test_value_widths_and_stability(vdtype):
 
 
 @pytest.mark.parametrize("kdtype", [np.uint32, np.float32, np.int64])
-def test_bit_windows_and_float_zeros(kdtype):
-    lengths = [100, 257, -5, 1, 999, 6001, 13_000]
+def test_bit_windows_and_float_zeros(kdtype, tiny_path):
+    lengths = [100, 257, -5, 1, 999, 6001, 13_000, 256, 31, 77]
     begins, ends, n = layout(lengths)
     bits = np.dtype(kdtype).itemsize * 8
     k = make_keys("entropy3", n, kdtype, seed=9)
@@ -124,7 +135,7 @@ def test_bit_windows_and_float_zeros(kdtype):
             check(k, v, begins, ends, descending=desc, begin_bit=b, end_bit=e)
 
 
-def test_many_small_segments_and_one_large():
+def test_many_small_segments_and_one_large(tiny_path):
     rng = np.random.default_rng(3)
     lengths = rng.integers(0, 40, size=20_000).tolist() + [1 << 20] + rng.integers(0, 3000, size=300).tolist()
     begins, ends, n = layout(lengths)
