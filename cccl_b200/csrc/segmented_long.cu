@@ -312,6 +312,17 @@ struct SegLongShape<uint64_t, 4>
   static constexpr int IPT = 20, MINB = 3, OPT = SEG_BASE | OPT_SHORT_WARP;
 };
 
+template <>
+struct SegLongShape<uint32_t, 8>
+{
+  static constexpr int IPT = 20, MINB = 3, OPT = SEG_BASE;
+};
+template <>
+struct SegLongShape<uint64_t, 8>
+{
+  static constexpr int IPT = 16, MINB = 3, OPT = SEG_BASE;
+};
+
 // phase 0: the table of the long segments (the per-segment kernel needs its overflow flag); phase 1: everything else
 template <class U, int VB>
 static cudaError_t seg_long_run(const SegLongPlan& p, int phase, cudaStream_t stream)
@@ -413,25 +424,34 @@ static cudaError_t seg_long_run(const SegLongPlan& p, int phase, cudaStream_t st
 
 bool seg_long_supported(int key_bytes, int value_bytes)
 {
-  return (key_bytes == 4 || key_bytes == 8) && (value_bytes == 0 || value_bytes == 4);
+  return (key_bytes == 4 || key_bytes == 8) && (value_bytes == 0 || value_bytes == 4 || value_bytes == 8);
+}
+
+template <class U>
+static uint32_t tile_items_of(int value_bytes)
+{
+  return 256u * uint32_t(value_bytes == 0   ? SegLongShape<U, 0>::IPT
+                         : value_bytes == 4 ? SegLongShape<U, 4>::IPT
+                                            : SegLongShape<U, 8>::IPT);
 }
 
 uint32_t seg_long_tile_items(int key_bytes, int value_bytes)
 {
-  if (key_bytes == 4)
-  {
-    return 256u * (value_bytes == 0 ? SegLongShape<uint32_t, 0>::IPT : SegLongShape<uint32_t, 4>::IPT);
-  }
-  return 256u * (value_bytes == 0 ? SegLongShape<uint64_t, 0>::IPT : SegLongShape<uint64_t, 4>::IPT);
+  return key_bytes == 4 ? tile_items_of<uint32_t>(value_bytes) : tile_items_of<uint64_t>(value_bytes);
+}
+
+template <class U>
+static cudaError_t seg_long_sort_v(const SegLongPlan& p, int phase, int value_bytes, cudaStream_t stream)
+{
+  return value_bytes == 0   ? seg_long_run<U, 0>(p, phase, stream)
+         : value_bytes == 4 ? seg_long_run<U, 4>(p, phase, stream)
+                            : seg_long_run<U, 8>(p, phase, stream);
 }
 
 cudaError_t seg_long_sort(const SegLongPlan& p, int phase, int key_bytes, int value_bytes, cudaStream_t stream)
 {
-  if (key_bytes == 4)
-  {
-    return value_bytes == 0 ? seg_long_run<uint32_t, 0>(p, phase, stream) : seg_long_run<uint32_t, 4>(p, phase, stream);
-  }
-  return value_bytes == 0 ? seg_long_run<uint64_t, 0>(p, phase, stream) : seg_long_run<uint64_t, 4>(p, phase, stream);
+  return key_bytes == 4 ? seg_long_sort_v<uint32_t>(p, phase, value_bytes, stream)
+                        : seg_long_sort_v<uint64_t>(p, phase, value_bytes, stream);
 }
 
 } // namespace b200rs

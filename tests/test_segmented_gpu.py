@@ -154,12 +154,12 @@ def test_segments_in_any_order_and_unsorted_offsets():
 
 
 @pytest.mark.parametrize("kdtype,vdtype", [(np.uint32, None), (np.uint32, np.uint32), (np.float32, np.uint32), (np.uint64, None),
-                                           (np.int64, np.uint32), (np.float64, None), (np.uint32, np.uint64)])
+                                           (np.int64, np.uint32), (np.float64, None), (np.uint32, np.uint64), (np.uint64, np.uint64), (np.uint32, np.uint16)])
 def test_long_segments_take_whole_grid_passes(kdtype, vdtype):
     """Segments longer than 2^16 items are sorted by whole-grid onesweep passes over all long segments at once
     (csrc/segmented_long.cu: tiles never straddle segments, per-segment bins and chained-scan rows); everything shorter
     by one CTA per segment in the same call.  Long segments at both ends, next to each other, listed out of order, around
-    the threshold and around multiples of the tile; +-0.0; both directions; a bit window; (u32, u64) pairs take the
+    the threshold and around multiples of the tile; +-0.0; both directions; a bit window; (u32, u16) pairs take the
     one-CTA path for every length (no whole-grid kernel for that width)."""
     lengths = [70_000, 65_536, 65_537, -3, 100, 0, 200_003, 44 * 256 * 6, 1, 5000, 131_072 + 11_264, -17, 90_001]
     begins, ends, n = layout(lengths)
