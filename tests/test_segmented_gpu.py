@@ -218,3 +218,44 @@ def test_segmented_sort_under_stream_capture_with_long_segments():
         for b, e in zip(begins.tolist(), ends.tolist()):
             assert_same_bits(to_host(d_ko, np.uint32, n)[b:e], ek[b:e], "captured segmented keys")
             assert_same_bits(to_host(d_vo, np.uint32, n)[b:e], ev[b:e], "captured segmented values")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_layouts_across_all_size_classes(seed):
+    """Randomised differential test: segment lengths drawn from a mixture that hits every size class and every class
+    boundary (0 / 1 / 32 / 256 / 257 / one tile +- 1 / several tiles / far above the whole-grid threshold), random gaps, random
+    listing order, random key / value types, direction and bit window -- against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    kdtype = [np.uint32, np.float32, np.int64, np.uint64, np.int32, np.float64][seed % 6]
+    vdtype = [None, np.uint32, np.uint64, np.uint32, np.uint8, None][seed % 6]
+    edges = [0, 1, 2, 31, 32, 33, 255, 256, 257, 1279, 1280, 1281, 2559, 2560, 2561, 5119, 5120, 5121, 8191, 8192, 8193, 11_263,
+             11_264, 11_265]
+    lengths = []
+    for _ in range(160):
+        r = rng.random()
+        if r < 0.35:
+            ln = int(rng.choice(edges))
+        elif r < 0.65:
+            ln = int(rng.integers(0, 300))
+        elif r < 0.85:
+            ln = int(rng.integers(300, 9000))
+        elif r < 0.97:
+            ln = int(rng.integers(9000, 60_000))
+        else:
+            ln = int(rng.integers(60_000, 300_000))
+        lengths.append(ln)
+        if rng.random() < 0.15:
+            lengths.append(-int(rng.integers(1, 40)))
+    begins, ends, n = layout(lengths)
+    perm = rng.permutation(len(begins))
+    begins, ends = begins[perm], ends[perm]
+    k = make_keys(["uniform", "entropy3", "few16"][seed % 3], n, kdtype, seed=seed)
+    if np.dtype(kdtype).kind == "f":
+        k[::11] = -0.0
+        k[::13] = 0.0
+    v = make_values(n, vdtype) if vdtype is not None else None
+    bits = np.dtype(kdtype).itemsize * 8
+    check(k, v, begins, ends, descending=bool(seed & 1), offset_dtype=[np.int64, np.int32][seed % 2])
+    b = int(rng.integers(0, bits - 1))
+    e = int(rng.integers(b + 1, bits + 1))
+    check(k, v, begins, ends, descending=not bool(seed & 1), begin_bit=b, end_bit=e)
