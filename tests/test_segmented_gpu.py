@@ -259,3 +259,61 @@ def test_random_layouts_across_all_size_classes(seed):
     b = int(rng.integers(0, bits - 1))
     e = int(rng.integers(b + 1, bits + 1))
     check(k, v, begins, ends, descending=not bool(seed & 1), begin_bit=b, end_bit=e)
+
+
+def test_python_mirror_of_cuda_compute_segmented_sort():
+    """cccl_b200.segmented_sort / make_segmented_sort with the reference's keyword interface and its own documentation
+    examples (python/cuda_cccl/tests/compute/examples/sort/segmented_sort_basic.py, segmented_sort_buffer.py,
+    segmented_sort_object.py): pointer form, DoubleBuffer form (result in .current()), reusable object with a size query."""
+    import cccl_b200
+    from cccl_b200 import DoubleBuffer, SortOrder
+
+    h_keys = np.array([9, 1, 5, 4, 2, 8, 7, 3, 6], dtype=np.int32)
+    h_vals = np.array([90, 10, 50, 40, 20, 80, 70, 30, 60], dtype=np.int32)
+    starts, ends = np.array([0, 3, 5], dtype=np.int64), np.array([3, 5, 9], dtype=np.int64)
+    d_k, d_v = torch.from_numpy(h_keys).cuda(), torch.from_numpy(h_vals).cuda()
+    d_s, d_e = torch.from_numpy(starts).cuda(), torch.from_numpy(ends).cuda()
+
+    def expected(reverse):
+        ek, ev = [], []
+        for s, e in zip(starts, ends):
+            pairs = sorted(zip(h_keys[s:e], h_vals[s:e]), key=lambda kv: kv[0], reverse=reverse)
+            ek += [k for k, _ in pairs]
+            ev += [v for _, v in pairs]
+        return np.array(ek, dtype=np.int32), np.array(ev, dtype=np.int32)
+
+    d_ko, d_vo = torch.empty_like(d_k), torch.empty_like(d_v)
+    cccl_b200.segmented_sort(d_in_keys=d_k, d_out_keys=d_ko, d_in_values=d_v, d_out_values=d_vo, num_items=9, num_segments=3,
+                             start_offsets_in=d_s, end_offsets_in=d_e, order=SortOrder.ASCENDING)
+    torch.cuda.synchronize()
+    ek, ev = expected(False)
+    assert np.array_equal(d_ko.cpu().numpy(), ek) and np.array_equal(d_vo.cpu().numpy(), ev)
+    assert np.array_equal(d_k.cpu().numpy(), h_keys), "pointer form must not write its input"
+
+    kdb = DoubleBuffer(d_k.clone(), torch.empty_like(d_k))
+    vdb = DoubleBuffer(d_v.clone(), torch.empty_like(d_v))
+    cccl_b200.segmented_sort(d_in_keys=kdb, d_out_keys=None, d_in_values=vdb, d_out_values=None, num_items=9, num_segments=3,
+                             start_offsets_in=d_s, end_offsets_in=d_e, order=SortOrder.DESCENDING)
+    torch.cuda.synchronize()
+    ek, ev = expected(True)
+    assert np.array_equal(kdb.current().cpu().numpy(), ek) and np.array_equal(vdb.current().cpu().numpy(), ev)
+
+    # reusable object, keys only, int32 offsets, a larger input that reaches every size class
+    begins, ends2, n = layout([70_000, 3, 300, 0, 9000])
+    k = make_keys("uniform", n, np.float32, seed=2)
+    dk, dko = torch.from_numpy(k).cuda(), torch.empty(n, dtype=torch.float32, device="cuda")
+    db = torch.from_numpy(begins.astype(np.int32)).cuda()
+    de = torch.from_numpy(ends2.astype(np.int32)).cuda()
+    sorter = cccl_b200.make_segmented_sort(d_in_keys=dk, d_out_keys=dko, start_offsets_in=db, end_offsets_in=de,
+                                           order=SortOrder.ASCENDING)
+    kw = dict(d_in_keys=dk, d_out_keys=dko, d_in_values=None, d_out_values=None, num_items=n, num_segments=len(begins),
+              start_offsets_in=db, end_offsets_in=de)
+    need = sorter(temp_storage=None, **kw)
+    assert need >= 1
+    temp = torch.empty(need, dtype=torch.uint8, device="cuda")
+    sorter(temp_storage=temp, **kw)
+    torch.cuda.synchronize()
+    want = oracle_segmented_sort(k, None, begins, ends2)
+    got = dko.cpu().numpy()
+    for b, e in zip(begins.tolist(), ends2.tolist()):
+        assert_same_bits(got[b:e], want[b:e], "python mirror, reusable object")
