@@ -57,15 +57,23 @@ __device__ __forceinline__ void single_tile_sort(const SingleTileArgs& a, const 
 
   U key[IPT];
   V val[VBYTES > 0 ? IPT : 1];
-  const uint32_t chunk = warp * 32 * IPT + lane;
+  // A partial tile is spread evenly over the warps: `rows` = ceil(n / 256) rows of 32 items per warp instead of IPT, so a
+  // 1 000-item segment costs every warp 4 ranked rows -- not warp 0 twenty and six warps twenty rows of padding.  Warp w
+  // still owns a contiguous chunk, so ranks follow (warp, row, lane) == input order.  Rows >= `rows` are skipped whole.
+  const uint32_t rows  = (n + ST_THREADS - 1) / ST_THREADS; // <= IPT, warp-uniform
+  const uint32_t chunk = warp * 32 * rows + lane;
 #pragma unroll
   for (int i = 0; i < IPT; ++i)
   {
     const uint32_t p = chunk + i * 32;
-    key[i]           = p < n ? twiddle_in(static_cast<const U*>(a.keys_in)[p], xf) : U(~U(0)); // padding sorts last
-    if (VBYTES > 0 && p < n)
+    key[i]           = U(~U(0)); // padding sorts last
+    if (uint32_t(i) < rows && p < n)
     {
-      val[i] = static_cast<const V*>(a.vals_in)[p];
+      key[i] = twiddle_in(static_cast<const U*>(a.keys_in)[p], xf);
+      if (VBYTES > 0)
+      {
+        val[i] = static_cast<const V*>(a.vals_in)[p];
+      }
     }
   }
 
@@ -86,18 +94,21 @@ __device__ __forceinline__ void single_tile_sort(const SingleTileArgs& a, const 
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
     {
-      const uint32_t d = pass_digit<FLOATK>(key[i], bit, mask, neg_zero, pos_zero);
-      uint32_t b, c;
-      match_digit_ballot_fma(d, a.all_ones, b, c);
-      const uint32_t before = __popc(b & c & lt_mask);
-      const uint32_t ctr    = s_mine + d * 2;
-      const uint32_t next   = ctr_ld<true>(ctr) + before + 1;
-      if ((b & c & gt_mask) == 0)
+      if (uint32_t(i) < rows)
       {
-        ctr_st<true>(ctr, next);
+        const uint32_t d = pass_digit<FLOATK>(key[i], bit, mask, neg_zero, pos_zero);
+        uint32_t b, c;
+        match_digit_ballot_fma(d, a.all_ones, b, c);
+        const uint32_t before = __popc(b & c & lt_mask);
+        const uint32_t ctr    = s_mine + d * 2;
+        const uint32_t next   = ctr_ld<true>(ctr) + before + 1;
+        if ((b & c & gt_mask) == 0)
+        {
+          ctr_st<true>(ctr, next);
+        }
+        __syncwarp(); // the next row's loads of this counter come after the leader's store (memory model, racecheck)
+        rank[i] = next - 1;
       }
-      __syncwarp(); // the next row's loads of this counter come after the leader's store (memory model, racecheck)
-      rank[i] = next - 1;
     }
     __syncthreads();
 
@@ -144,23 +155,29 @@ __device__ __forceinline__ void single_tile_sort(const SingleTileArgs& a, const 
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
     {
-      const uint32_t d = pass_digit<FLOATK>(key[i], bit, mask, neg_zero, pos_zero);
-      const uint32_t r = rank[i] + ctr_ld<true>(s_mine + d * 2);
-      sts_t<U>(s_keys + r * uint32_t(sizeof(U)), key[i]);
-      if (VBYTES > 0)
+      if (uint32_t(i) < rows)
       {
-        sts_t<V>(s_vals + r * uint32_t(sizeof(V)), val[i]);
+        const uint32_t d = pass_digit<FLOATK>(key[i], bit, mask, neg_zero, pos_zero);
+        const uint32_t r = rank[i] + ctr_ld<true>(s_mine + d * 2);
+        sts_t<U>(s_keys + r * uint32_t(sizeof(U)), key[i]);
+        if (VBYTES > 0)
+        {
+          sts_t<V>(s_vals + r * uint32_t(sizeof(V)), val[i]);
+        }
       }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < IPT; ++i)
     {
-      const uint32_t p = chunk + i * 32;
-      key[i]           = lds_t<U>(s_keys + p * uint32_t(sizeof(U)));
-      if (VBYTES > 0)
+      if (uint32_t(i) < rows)
       {
-        val[i] = lds_t<V>(s_vals + p * uint32_t(sizeof(V)));
+        const uint32_t p = chunk + i * 32;
+        key[i]           = lds_t<U>(s_keys + p * uint32_t(sizeof(U)));
+        if (VBYTES > 0)
+        {
+          val[i] = lds_t<V>(s_vals + p * uint32_t(sizeof(V)));
+        }
       }
     }
   }
@@ -169,7 +186,7 @@ __device__ __forceinline__ void single_tile_sort(const SingleTileArgs& a, const 
   for (int i = 0; i < IPT; ++i)
   {
     const uint32_t p = chunk + i * 32;
-    if (p < n)
+    if (uint32_t(i) < rows && p < n)
     {
       static_cast<U*>(a.keys_out)[p] = twiddle_out(key[i], xf);
       if (VBYTES > 0)
