@@ -45,6 +45,7 @@ struct SegArgs
   const SegLongCtl* long_ctl; // != nullptr: segments longer than long_min are sorted by segmented_long.cu
   uint32_t long_min;
   uint32_t tiny_max; // segments of at most this many items are sorted by segmented_tiny_kernel (0 = none)
+  uint32_t batch;    // segments a CTA of segmented_sort_kernel examines at a time (1 .. ST_THREADS)
 };
 
 __device__ __forceinline__ long long load_offset(const void* p, long long i, int bytes)
@@ -236,23 +237,42 @@ __global__ void __launch_bounds__(ST_THREADS, 3) segmented_sort_kernel(const Seg
   __shared__ uint32_t s_excl[RADIX];
   __shared__ uint32_t s_hist[MAXPASS][RADIX]; // long segments: digit counts of every pass, from ONE read of the segment
   const uint32_t sbase = uint32_t(__cvta_generic_to_shared(seg_smem));
-  for (long long seg = blockIdx.x; seg < a.num_segments; seg += gridDim.x)
+  // A CTA looks at a.batch segments at a time, one per thread, and keeps the ones that are its business (not empty, not
+  // tiny, not long): with 168 K tiny segments the kernel used to spend 0.22 ms on every thread of every CTA loading the
+  // offsets of segments it then skipped.  The host sizes the batch so that there are still >= 16 batches per SM.
+  __shared__ uint32_t s_todo[ST_THREADS];
+  __shared__ uint32_t s_ntodo;
+  const bool long_on = a.long_ctl != nullptr && a.long_ctl->overflow == 0;
+  for (long long batch = (long long) blockIdx.x * a.batch; batch < a.num_segments; batch += (long long) gridDim.x * a.batch)
   {
+    __syncthreads(); // the previous batch's list is dead
+    if (threadIdx.x == 0)
+    {
+      s_ntodo = 0;
+    }
+    __syncthreads();
+    {
+      const long long seg = batch + threadIdx.x;
+      if (threadIdx.x < a.batch && seg < a.num_segments)
+      {
+        const long long b0   = load_offset(a.begin_offsets, seg, a.offset_bytes);
+        const long long e0   = load_offset(a.end_offsets, seg, a.offset_bytes);
+        const long long len0 = a.offset_bytes == 8 ? e0 - b0 : (long long) (int) (uint32_t(e0) - uint32_t(b0));
+        // long: whole-grid passes (segmented_long.cu); tiny: one warp per segment (segmented_tiny_kernel)
+        if (len0 > (long long) a.tiny_max && !(long_on && len0 > (long long) a.long_min))
+        {
+          s_todo[atomicAdd(&s_ntodo, 1u)] = threadIdx.x;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t ntodo = s_ntodo;
+  for (uint32_t q = 0; q < ntodo; ++q)
+  {
+    const long long seg = batch + s_todo[q];
     const long long b   = load_offset(a.begin_offsets, seg, a.offset_bytes);
     const long long e   = load_offset(a.end_offsets, seg, a.offset_bytes);
     const long long len = a.offset_bytes == 8 ? e - b : (long long) (int) (uint32_t(e) - uint32_t(b));
-    if (len <= 0)
-    {
-      continue;
-    }
-    if (a.long_ctl != nullptr && len > (long long) a.long_min && a.long_ctl->overflow == 0)
-    {
-      continue; // whole-grid passes (segmented_long.cu)
-    }
-    if (len <= (long long) a.tiny_max)
-    {
-      continue; // one warp per segment (segmented_tiny_kernel)
-    }
     const U* kin = static_cast<const U*>(a.keys_in) + b;
     U* kout      = static_cast<U*>(a.keys_out) + b;
     const V* vin = VBYTES > 0 ? static_cast<const V*>(a.vals_in) + b : nullptr;
@@ -339,6 +359,7 @@ __global__ void __launch_bounds__(ST_THREADS, 3) segmented_sort_kernel(const Seg
       src  = dst;
       vsrc = vdst;
     }
+  }
   }
 }
 
@@ -555,10 +576,15 @@ static cudaError_t launch_seg(const SegArgs& a, int sms, cudaStream_t stream)
       return e;
     }
   }
-  // one CTA per segment; more segments than this grid are taken round-robin
-  const long long cap = (long long) sms * 64;
-  const unsigned grid = unsigned(a.num_segments < cap ? a.num_segments : cap);
-  kernel<<<grid, ST_THREADS, L::BYTES, stream>>>(a);
+  // one CTA per batch of segments (taken round-robin); a CTA sorts the short segments of its batches one by one.  Batch
+  // size: as large as leaves >= 16 batches per SM, at most one segment per thread
+  SegArgs b               = a;
+  const long long per     = a.num_segments / ((long long) sms * 16);
+  b.batch                 = uint32_t(per < 1 ? 1 : (per > ST_THREADS ? ST_THREADS : per));
+  const long long cap     = (long long) sms * 64;
+  const long long batches = (a.num_segments + b.batch - 1) / b.batch;
+  const unsigned grid     = unsigned(batches < cap ? batches : cap);
+  kernel<<<grid, ST_THREADS, L::BYTES, stream>>>(b);
   return cudaPeekAtLastError();
 }
 

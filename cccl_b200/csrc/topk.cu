@@ -159,6 +159,11 @@ topk_filter_body(const U* keys, U* keys_out, const typename value_of<VBYTES>::ty
       better |= (i < n && t < kth) ? (1u << j) : 0u;
       tie |= (i < n && t == kth) ? (1u << j) : 0u;
     }
+    // almost every chunk selects nothing when K << n: one barrier decides, the scans below are skipped
+    if (__syncthreads_or((better | (need_eq != 0 ? tie : 0u)) != 0) == 0)
+    {
+      continue;
+    }
     uint32_t take = better;
     if (need_eq != 0 && __syncthreads_or(tie != 0))
     {
