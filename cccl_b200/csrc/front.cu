@@ -84,6 +84,19 @@ extern "C" B200RS_API int b200rs_sort_inplace(
   {
     return rc;
   }
+  if (temp_bytes == 1)
+  {
+    // At most one tile (the only non-empty full-width sort with a 1-byte temp): the single-CTA kernel reads every item
+    // before it writes any, so it sorts IN PLACE -- no scratch allocation, no copy back.
+    int sel = 0;
+    rc      = b200rs_sort(d_keys /* never dereferenced */, &temp_bytes, d_keys, d_keys, d_values, d_values, num_items,
+                          key_kind, key_bytes, value_bytes, 0, end_bit, descending, 1, &sel, stream_);
+    if (rc == 0 && synchronize)
+    {
+      rc = int(cudaStreamSynchronize(stream));
+    }
+    return rc;
+  }
   const size_t keys_scratch = round_up(size_t(num_items) * key_bytes, 128);
   const size_t vals_scratch = round_up(size_t(num_items) * value_bytes, 128);
   const size_t total        = keys_scratch + vals_scratch + temp_bytes;
