@@ -96,3 +96,52 @@ def test_product_does_not_touch_the_oracle():
                     if re.search(r"liboracle|oracle_lib|oracle/|ref_thrust", txt):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+# ---- the adjacent callers: size queries and argument checks run without a GPU too
+def _seg_query(n, segs, kb=4, vb=4, begin=0, end=None, offset_bytes=8):
+    lib = _native.lib()
+    need = ctypes.c_size_t(0)
+    rc = lib.b200rs_segmented_sort(None, ctypes.byref(need), None, None, None, None, n, segs, None, None, offset_bytes, 0, kb, vb,
+                                   begin, kb * 8 if end is None else end, 0, None)
+    return rc, need.value
+
+
+def test_segmented_size_query_and_argument_checks():
+    rc, small = _seg_query(1000, 10)
+    assert rc == 0 and small == 1  # at most one tile in total: every segment is sorted in shared memory, no scratch
+    rc, big = _seg_query(1 << 24, 1000)
+    assert rc == 0
+    # scratch copies of keys and values (what the reference needs) + the worst-case plan of the whole-grid path
+    assert (1 << 24) * 8 <= big <= int((1 << 24) * 8 * 1.4)
+    assert _seg_query(1 << 24, 1000) == (0, big)  # pure
+    rc1, one_pass = _seg_query(1 << 24, 1000, begin=3, end=9)
+    assert rc1 == 0 and one_pass < big  # a single pass needs no scratch copies
+    lib = _native.lib()
+    lib.b200rs_set_segmented_long_min(0)
+    try:
+        rc, off = _seg_query(1 << 24, 1000)
+        assert rc == 0 and off < big and off >= (1 << 24) * 8  # without the whole-grid path: the scratch copies only
+    finally:
+        lib.b200rs_set_segmented_long_min(1)
+    assert _seg_query(10, 1, offset_bytes=2)[0] == 1  # cudaErrorInvalidValue
+    assert _seg_query(10, 1, kb=3)[0] == 801  # cudaErrorNotSupported
+    assert _seg_query(10, 1, begin=5, end=3)[0] == 1
+
+
+def test_topk_size_query_and_argument_checks():
+    lib = _native.lib()
+    need = ctypes.c_size_t(0)
+
+    def q(n, k, kb=4, vb=0, kind=0):
+        rc = lib.b200rs_topk(None, ctypes.byref(need), None, None, None, None, n, k, kind, kb, vb, 1, None)
+        return rc, need.value
+
+    assert q(0, 5) == (0, 1) and q(100, 0) == (0, 1)
+    rc, a = q(1 << 20, 10)
+    assert rc == 0 and a > 1
+    assert q(1 << 20, 1 << 19) == (0, a)  # K does not change the temporary storage
+    rc, b = q(1 << 24, 10)
+    assert rc == 0 and a < b <= (1 << 24) * 4  # the candidate buffer: a fraction of the keys, never a copy of them
+    assert q(10, 1, kb=3)[0] == 801 and q(10, 1, vb=12)[0] == 801 and q(10, 1, kind=7)[0] == 1
+    assert lib.b200rs_topk(None, None, None, None, None, None, 10, 1, 0, 4, 0, 1, None) == 1
