@@ -13,7 +13,7 @@
 //   SortKeys             pointer :3034  DoubleBuffer :3644   env :3138 / :3743
 //   SortKeysDescending   pointer :4211  DoubleBuffer :4669   env :4310 / :4768
 // Decomposer overloads for user-defined key types (:671, :905, :1359, :1565 and the Descending / SortKeys twins, with and
-// without a bit window) and 128-bit integer keys go through b200rs_sort_fields: the members the decomposer returns are
+// without a bit window, temp-storage and env forms) and 128-bit integer keys go through b200rs_sort_fields: the members the decomposer returns are
 // sorted as a chain of stable passes, least significant member first (see cccl_b200/csrc/fields.cu).
 //
 // Semantics kept from the reference:
@@ -783,6 +783,96 @@ struct DeviceRadixSort
   B200RS_DECOMPOSER_OVERLOADS(SortPairs, SortKeys, false)
   B200RS_DECOMPOSER_OVERLOADS(SortPairsDescending, SortKeysDescending, true)
 #undef B200RS_DECOMPOSER_OVERLOADS
+
+  // ------------------------------------------------------------------ decomposer + environment overloads
+  // reference: the env twins of the decomposer overloads (catch2_test_device_radix_sort_env_api.cu:227-400 passes a
+  // decomposer and a cuda::stream_ref, with and without a bit window, pointer and DoubleBuffer forms): temporary storage
+  // from the stream-ordered pool, everything else as the overloads above
+#define B200RS_DECOMPOSER_ENV_GUARD                                                                                    \
+  std::enable_if_t<!std::is_convertible<DecomposerT, int>::value && !detail::b200rs_is_env<DecomposerT>::value         \
+                     && detail::b200rs_is_env<EnvT>::value && std::is_integral<NumItemsT>::value,                      \
+                   int> = 0
+#define B200RS_DECOMPOSER_ENV_OVERLOADS(PAIRS_NAME, KEYS_NAME)                                                         \
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename DecomposerT, typename EnvT = stream_env,       \
+            B200RS_DECOMPOSER_ENV_GUARD>                                                                               \
+  [[nodiscard]] static cudaError_t PAIRS_NAME(const KeyT* d_keys_in, KeyT* d_keys_out, const ValueT* d_values_in,      \
+                                              ValueT* d_values_out, NumItemsT num_items, DecomposerT decomposer,      \
+                                              const EnvT& env = {})                                                    \
+  {                                                                                                                    \
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {             \
+      return PAIRS_NAME(t, b, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items, decomposer, s);             \
+    });                                                                                                                \
+  }                                                                                                                    \
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename DecomposerT, typename EnvT = stream_env,       \
+            B200RS_DECOMPOSER_ENV_GUARD>                                                                               \
+  [[nodiscard]] static cudaError_t PAIRS_NAME(const KeyT* d_keys_in, KeyT* d_keys_out, const ValueT* d_values_in,      \
+                                              ValueT* d_values_out, NumItemsT num_items, DecomposerT decomposer,      \
+                                              int begin_bit, int end_bit, const EnvT& env = {})                        \
+  {                                                                                                                    \
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {             \
+      return PAIRS_NAME(t, b, d_keys_in, d_keys_out, d_values_in, d_values_out, num_items, decomposer, begin_bit,      \
+                        end_bit, s);                                                                                   \
+    });                                                                                                                \
+  }                                                                                                                    \
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename DecomposerT, typename EnvT = stream_env,       \
+            B200RS_DECOMPOSER_ENV_GUARD>                                                                               \
+  [[nodiscard]] static cudaError_t PAIRS_NAME(DoubleBuffer<KeyT>& d_keys, DoubleBuffer<ValueT>& d_values,              \
+                                              NumItemsT num_items, DecomposerT decomposer, const EnvT& env = {})       \
+  {                                                                                                                    \
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {             \
+      return PAIRS_NAME(t, b, d_keys, d_values, num_items, decomposer, s);                                             \
+    });                                                                                                                \
+  }                                                                                                                    \
+  template <typename KeyT, typename ValueT, typename NumItemsT, typename DecomposerT, typename EnvT = stream_env,       \
+            B200RS_DECOMPOSER_ENV_GUARD>                                                                               \
+  [[nodiscard]] static cudaError_t PAIRS_NAME(DoubleBuffer<KeyT>& d_keys, DoubleBuffer<ValueT>& d_values,              \
+                                              NumItemsT num_items, DecomposerT decomposer, int begin_bit, int end_bit, \
+                                              const EnvT& env = {})                                                    \
+  {                                                                                                                    \
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {             \
+      return PAIRS_NAME(t, b, d_keys, d_values, num_items, decomposer, begin_bit, end_bit, s);                         \
+    });                                                                                                                \
+  }                                                                                                                    \
+  template <typename KeyT, typename NumItemsT, typename DecomposerT, typename EnvT = stream_env,                        \
+            B200RS_DECOMPOSER_ENV_GUARD>                                                                               \
+  [[nodiscard]] static cudaError_t KEYS_NAME(const KeyT* d_keys_in, KeyT* d_keys_out, NumItemsT num_items,             \
+                                             DecomposerT decomposer, const EnvT& env = {})                             \
+  {                                                                                                                    \
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {             \
+      return KEYS_NAME(t, b, d_keys_in, d_keys_out, num_items, decomposer, s);                                         \
+    });                                                                                                                \
+  }                                                                                                                    \
+  template <typename KeyT, typename NumItemsT, typename DecomposerT, typename EnvT = stream_env,                        \
+            B200RS_DECOMPOSER_ENV_GUARD>                                                                               \
+  [[nodiscard]] static cudaError_t KEYS_NAME(const KeyT* d_keys_in, KeyT* d_keys_out, NumItemsT num_items,             \
+                                             DecomposerT decomposer, int begin_bit, int end_bit, const EnvT& env = {}) \
+  {                                                                                                                    \
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {             \
+      return KEYS_NAME(t, b, d_keys_in, d_keys_out, num_items, decomposer, begin_bit, end_bit, s);                     \
+    });                                                                                                                \
+  }                                                                                                                    \
+  template <typename KeyT, typename NumItemsT, typename DecomposerT, typename EnvT = stream_env,                        \
+            B200RS_DECOMPOSER_ENV_GUARD>                                                                               \
+  [[nodiscard]] static cudaError_t KEYS_NAME(DoubleBuffer<KeyT>& d_keys, NumItemsT num_items, DecomposerT decomposer,  \
+                                             const EnvT& env = {})                                                     \
+  {                                                                                                                    \
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {             \
+      return KEYS_NAME(t, b, d_keys, num_items, decomposer, s);                                                        \
+    });                                                                                                                \
+  }                                                                                                                    \
+  template <typename KeyT, typename NumItemsT, typename DecomposerT, typename EnvT = stream_env,                        \
+            B200RS_DECOMPOSER_ENV_GUARD>                                                                               \
+  [[nodiscard]] static cudaError_t KEYS_NAME(DoubleBuffer<KeyT>& d_keys, NumItemsT num_items, DecomposerT decomposer,  \
+                                             int begin_bit, int end_bit, const EnvT& env = {})                         \
+  {                                                                                                                    \
+    return detail::b200rs_with_env(detail::b200rs_env_view(env), [&](void* t, size_t& b, cudaStream_t s) {             \
+      return KEYS_NAME(t, b, d_keys, num_items, decomposer, begin_bit, end_bit, s);                                    \
+    });                                                                                                                \
+  }
+  B200RS_DECOMPOSER_ENV_OVERLOADS(SortPairs, SortKeys)
+  B200RS_DECOMPOSER_ENV_OVERLOADS(SortPairsDescending, SortKeysDescending)
+#undef B200RS_DECOMPOSER_ENV_OVERLOADS
+#undef B200RS_DECOMPOSER_ENV_GUARD
 };
 
 } // namespace cub

@@ -556,6 +556,47 @@ void decomposer_cases()
     REQUIRE(same_custom(o.host(), {{-2.5f, 0}, {+0.0f, 1}, {-0.0f, 2}, {+1.1f, 3}, {+2.5f, 4}, {+3.7f, 5}}));
     REQUIRE((vo.host() == std::vector<int>{0, 1, 2, 3, 4, 5}));
   }
+  { // decomposer + environment (catch2_test_device_radix_sort_env_api.cu:227-400): cuda::stream_ref as the env, with and
+    // without a bit window, pointer and DoubleBuffer forms, keys and pairs
+    cudaStream_t stream;
+    cudaStreamCreate(&stream);
+    cuda::stream_ref stream_ref{stream};
+    const std::vector<custom_t> sorted{{-2.5f, 0}, {+0.0f, 1}, {-0.0f, 2}, {+1.1f, 3}, {+2.5f, 4}, {+3.7f, 5}};
+    dev<custom_t> k(in), o(in.size());
+    REQUIRE(cub::DeviceRadixSort::SortKeys(k.p, o.p, 6, decomposer_t{}, stream_ref) == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    REQUIRE(same_custom(o.host(), sorted));
+    dev<custom_t> o2(in.size());
+    REQUIRE(cub::DeviceRadixSort::SortKeys(k.p, o2.p, 6, decomposer_t{}, 0, 96, stream_ref) == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    REQUIRE(same_custom(o2.host(), sorted));
+    dev<int> v(std::vector<int>{4, 0, 3, 1, 2, 5}), vo(6);
+    dev<custom_t> o3(in.size());
+    REQUIRE(cub::DeviceRadixSort::SortPairs(k.p, o3.p, v.p, vo.p, 6, decomposer_t{}, stream_ref) == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    REQUIRE(same_custom(o3.host(), sorted));
+    REQUIRE((vo.host() == std::vector<int>{0, 1, 2, 3, 4, 5}));
+    dev<custom_t> ka(in), kb(in.size());
+    dev<int> va(std::vector<int>{4, 0, 3, 1, 2, 5}), vb(6);
+    cub::DoubleBuffer<custom_t> dk(ka.p, kb.p);
+    cub::DoubleBuffer<int> dv(va.p, vb.p);
+    REQUIRE(cub::DeviceRadixSort::SortPairsDescending(dk, dv, 6, decomposer_t{}, 0, 96, stream_ref) == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    std::vector<custom_t> got(6);
+    std::vector<int> gotv(6);
+    cudaMemcpy(got.data(), dk.Current(), 6 * sizeof(custom_t), cudaMemcpyDeviceToHost);
+    cudaMemcpy(gotv.data(), dv.Current(), 6 * sizeof(int), cudaMemcpyDeviceToHost);
+    // -0.0 == +0.0 in the float member, so the two zeros are ordered by the second member (descending: 2 before 1)
+    REQUIRE(same_custom(got, {{+3.7f, 5}, {+2.5f, 4}, {+1.1f, 3}, {-0.0f, 2}, {+0.0f, 1}, {-2.5f, 0}}));
+    REQUIRE((gotv == std::vector<int>{5, 4, 3, 2, 1, 0}));
+    cub::DoubleBuffer<custom_t> dk2(ka.p, kb.p);
+    cudaMemcpy(ka.p, in.data(), 6 * sizeof(custom_t), cudaMemcpyHostToDevice);
+    REQUIRE(cub::DeviceRadixSort::SortKeys(dk2, 6, decomposer_t{}, stream_ref) == cudaSuccess);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(got.data(), dk2.Current(), 6 * sizeof(custom_t), cudaMemcpyDeviceToHost);
+    REQUIRE(same_custom(got, sorted));
+    cudaStreamDestroy(stream);
+  }
   // randomized: (float, long long) keys with many ties against a host stable sort of the tuple order; a bit window that
   // cuts into both members; DoubleBuffer form
   std::mt19937_64 rng(2024);
