@@ -144,3 +144,14 @@ def oracle_segmented_sort(keys: np.ndarray, values, begin_offsets, end_offsets, 
             kout[b:e], vout[b:e] = oracle_sort(keys[b:e], values[b:e], descending=descending, begin_bit=begin_bit,
                                                end_bit=end_bit, segment=True)
     return (kout, vout) if values is not None else kout
+
+
+def oracle_topk(keys: np.ndarray, values: np.ndarray | None, k: int, largest: bool):
+    """CPU restatement of cub::DeviceTopK (cub/cub/device/device_topk.cuh:179-200): the K best items, here in sorted order
+    (the reference returns them unordered and any subset of the ties of the K-th key; its own tests sort before comparing,
+    cub/test/catch2_test_device_topk_api.cu:203-210).  Stable oracle sort in the requested direction, first min(k, n) items."""
+    kk = min(int(k), keys.shape[0])
+    if values is None:
+        return oracle_sort(keys, descending=largest)[:kk]
+    sk, sv = oracle_sort(keys, values, descending=largest)
+    return sk[:kk], sv[:kk]

@@ -141,3 +141,18 @@ def test_segmented_oracle_against_reference_cub_fixtures():
         else:
             ok = oracle_segmented_sort(z["keys_in"], None, z["begin_offsets"], z["end_offsets"], **kw)
         assert np.array_equal(ok.view(np.uint8), z["keys_out"].view(np.uint8)), f
+
+
+def test_topk_oracle_against_the_reference_documentation_examples():
+    """cub/test/catch2_test_device_topk_api.cu:115-158 (MinPairs, k = 4) and :165-210 (MaxPairs, k = 4): keys
+    {5, -3, 1, 7, 8, 2, 4, 6} with their indices as values."""
+    from oracle_lib import oracle_topk
+
+    keys = np.array([5, -3, 1, 7, 8, 2, 4, 6], dtype=np.int32)
+    vals = np.arange(8, dtype=np.int32)
+    k, v = oracle_topk(keys, vals, 4, largest=False)
+    assert k.tolist() == [-3, 1, 2, 4] and v.tolist() == [1, 2, 5, 6]
+    k, v = oracle_topk(keys, vals, 4, largest=True)
+    assert k.tolist() == [8, 7, 6, 5] and v.tolist() == [4, 3, 7, 0]
+    assert oracle_topk(keys, None, 100, largest=True).tolist() == sorted(keys.tolist(), reverse=True)  # k capped to n
+    assert oracle_topk(keys, None, 0, largest=True).size == 0
